@@ -1,0 +1,192 @@
+/*
+ * lsf.h -- C ABI of the B200 line front end ("lane-slam front", lsf).
+ *
+ * Drop-in boundary for the per-frame line path of mandanasmi/lane-slam.  Every entry point
+ * names the reference interface it replaces (file:line relative to the reference repo).
+ * Plain pointers and sizes only; no C++/torch types.  All functions return 0 (LSF_OK) or a
+ * negative lsf_status; no exception crosses the boundary; lsf_last_error() gives the text.
+ *
+ * Ownership: the caller allocates every output with an explicit capacity; the library owns
+ * only device scratch inside lsf_ctx.  A ctx is single-owner / not re-entrant (the reference
+ * admits one processImage_ at a time: src/line_detector/src/line_detector_node.py:129-139);
+ * lsf_set_color_transform is the only call allowed concurrently with a batch.
+ */
+#ifndef LSF_H
+#define LSF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LSF_API __attribute__((visibility("default")))
+#else
+#define LSF_API
+#endif
+
+typedef enum lsf_status {
+    LSF_OK = 0,
+    LSF_E_CONFIG = -1,   /* bad configuration      (reference: ValueError, duckietown_utils/parameters.py:5-23) */
+    LSF_E_ARG = -2,      /* bad argument           (reference: Exception, line_detector_lsd.py:49) */
+    LSF_E_CAPACITY = -3, /* caller/scratch capacity too small; lsf_last_error names the required size */
+    LSF_E_CUDA = -4,     /* CUDA runtime / driver failure, or no sm_100 device */
+    LSF_E_NCCL = -5,
+    LSF_E_INTERNAL = -6
+} lsf_status;
+
+typedef enum lsf_mem_kind { LSF_MEM_HOST = 0, LSF_MEM_PINNED = 1, LSF_MEM_DEVICE = 2 } lsf_mem_kind;
+
+/* Segment.msg:1-3 */
+enum { LSF_WHITE = 0, LSF_YELLOW = 1, LSF_RED = 2 };
+
+/*
+ * POD mirror of the YAML / rosparam configuration of the path:
+ *   line_detector_node/default.yaml:1-23 (img_size, top_cutoff, detector configuration),
+ *   AntiInstagramTransform (line_detector_node.py:112-114), camera_intrinsic/default.yaml:1-20,
+ *   camera_extrinsic/default.yaml:1, line_sanity_node.py:17-23.
+ * LSD itself runs with OpenCV's defaults + LSD_REFINE_ADV (line_detector_lsd.py:65); those are
+ * fixed in the kernels (scale 0.8, sigma_scale 0.6, quant 2, ang_th 22.5, log_eps 0, density 0.7, 1024 bins).
+ */
+typedef struct lsf_config {
+    int32_t img_h, img_w;        /* img_size = [h, w]; frames of another size are nearest-resized to it */
+    int32_t top_cutoff;          /* rows [0, top_cutoff) of the resized frame are dropped */
+    int32_t hsv_lo[4][3];        /* white1, yellow1, red1, red3 */
+    int32_t hsv_hi[4][3];        /* white2, yellow2, red2, red4 */
+    int32_t dilation_kernel_size;/* 3 (cross) or 1 (none); other sizes -> LSF_E_CONFIG */
+    int32_t canny_lo, canny_hi;  /* canny_thresholds */
+    float ai_scale[3], ai_shift[3]; /* AntiInstagram scale / shift per B,G,R channel; identity = 1 / 0 */
+    double K[9], D[5], R[9], P[12]; /* CameraInfo */
+    int32_t cam_w, cam_h;
+    double Hgnd[9];              /* ground homography */
+    double lanewidth, linewidth_white, linewidth_yellow, d_min, d_max, phi_min, phi_max;
+    /* capacities (0 = library default) */
+    int32_t max_batch;           /* frames per call the scratch is sized for */
+    int32_t max_src_h, max_src_w;/* largest input frame */
+    int32_t max_segments_per_color; /* per frame and colour */
+    int32_t max_pixels_per_color;   /* LSD support pixels per frame and colour */
+    int32_t device;              /* CUDA device ordinal */
+    int32_t reserved[7];
+} lsf_config;
+
+/*
+ * SoA segment batch.  Order = frame, then white / yellow / red, then LSD acceptance order
+ * (line_detector_node.py:197-205).  Arrays the caller leaves NULL are skipped.
+ * All arrays live in `mem` (host/pinned or device).
+ */
+typedef struct lsf_segments {
+    int32_t mem;               /* lsf_mem_kind of every pointer below */
+    int32_t capacity;          /* rows available in the per-segment arrays */
+    int32_t n_frames;          /* out */
+    int32_t n_segments;        /* out: total rows written */
+    int32_t *counts;           /* [n_frames][3] segments per frame and colour (Detections.lines lengths) */
+    int32_t *frame_offset;     /* [n_frames+1] first row of every frame */
+    uint8_t *color;            /* [S]      Segment.color */
+    float *lines_px;           /* [S][4]   Detections.lines: x1,y1,x2,y2 in cropped-image pixels, after endpoint ordering */
+    double *normals;           /* [S][2]   Detections.normals (float64 in the reference) */
+    float *centers;            /* [S][2]   Detections.centers */
+    float *pixels_normalized;  /* [S][4]   Segment.pixels_normalized (Vector2D float32) */
+    float *normal_f32;         /* [S][2]   Segment.normal (Vector2D float32) */
+    double *ground;            /* [S][4]   Segment.points x1,y1,x2,y2 (geometry_msgs/Point float64, z = 0) */
+    uint8_t *keep;             /* [S]      1 iff line_sanity keeps the segment */
+    uint8_t *desc;             /* [S][32]  LBD binary descriptor */
+    int32_t *match_idx;        /* [S][k]   kNN train index in the map (or -1) */
+    int32_t *match_dist;       /* [S][k]   Hamming distance (or -1) */
+} lsf_segments;
+
+typedef struct lsf_ctx lsf_ctx;
+
+/* stage selectors for lsf_front_end_batch */
+enum {
+    LSF_STAGE_DETECT = 1,   /* line_detector_node: resize/crop/colour-correct, HSV masks, Canny, 3x LSD, normals */
+    LSF_STAGE_GROUND = 2,   /* ground_projection_node + line_sanity_node */
+    LSF_STAGE_DESCRIBE = 4, /* LSDDetectorC KeyLine fill + BinaryDescriptor::compute */
+    LSF_STAGE_MATCH = 8     /* BinaryDescriptorMatcher::knnMatch against the ctx map */
+};
+
+/* debug / parity taps (dense per-frame maps, one byte per pixel, 0/255 or label values) */
+enum {
+    LSF_TAP_IMAGE = 0,     /* processed BGR image [h][w][3] (after resize/crop/colour correction) */
+    LSF_TAP_LABELS = 1,    /* bit0 white, bit1 yellow, bit2 red raw inRange masks; bits 4-5 Canny NMS class (0,1,2) */
+    LSF_TAP_EDGES = 2,     /* cv2.Canny output 0/255 */
+    LSF_TAP_BW_WHITE = 3, LSF_TAP_BW_YELLOW = 4, LSF_TAP_BW_RED = 5,      /* Detections.area */
+    LSF_TAP_EC_WHITE = 6, LSF_TAP_EC_YELLOW = 7, LSF_TAP_EC_RED = 8,      /* edge_color fed to LSD */
+    LSF_TAP_GRAY = 9,      /* BGR2GRAY [h][w] */
+    LSF_TAP_DX = 10, LSF_TAP_DY = 11 /* int16 [h][w] Sobel of the 5x5-blurred gray (descriptor path) */
+};
+
+/* Fill *cfg with the reference defaults (default.yaml files cited above) for a src_h x src_w camera. */
+LSF_API int lsf_default_config(lsf_config *cfg);
+
+/* Replaces: instantiate(c[0], c[1]) / LineDetectorLSD.__init__ (line_detector_node.py:83-90,
+ * line_detector_lsd.py:14-36) + GroundProjection.__init__ (GroundProjection.py:17-36) +
+ * LineSanityNode.__init__ (line_sanity_node.py:15-23). */
+LSF_API int lsf_create(const lsf_config *cfg, lsf_ctx **out);
+LSF_API void lsf_destroy(lsf_ctx *ctx);
+LSF_API const char *lsf_last_error(const lsf_ctx *ctx); /* ctx may be NULL: last create() error */
+
+/* Replaces: LineDetectorNode.cbTransform (line_detector_node.py:112-114).  Takes effect next batch. */
+LSF_API int lsf_set_color_transform(lsf_ctx *ctx, const float scale[3], const float shift[3]);
+
+/* Replaces: LineDetectorNode.processImage_ (line_detector_node.py:141-213) for n frames at once,
+ * i.e. cv2.resize/crop, AntiInstagram.applyTransform + convertScaleAbs, LineDetectorLSD.setImage and
+ * detectLines x3 (line_detector_lsd.py:38-139), normalisation and toSegmentMsg (:195-205, :251-265);
+ * with stages |= GROUND also GroundProjectionNode.lineseglist_cb (ground_projection_node.py:55-65) and
+ * LineSanityNode.processSegmentList (line_sanity_node.py:48-72); with DESCRIBE also
+ * LSDDetectorC::detectImpl KeyLine fill (LSDDetector_custom.cpp:176-197) and BinaryDescriptor::compute
+ * (binary_descriptor_custom.cpp:539-687); with MATCH also BinaryDescriptorMatcher::knnMatch
+ * (binary_descriptor_matcher.cpp:258-335) of every segment against the ctx map (k neighbours).
+ * bgr: n frames of src_h x src_w x 3 bytes, row pitch `pitch` bytes, frame stride src_h*pitch. */
+LSF_API int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int src_h, int src_w, size_t pitch,
+                                int mem_kind, int stages, int k, lsf_segments *out);
+
+/* = lsf_front_end_batch(..., LSF_STAGE_DETECT, 0, out) */
+LSF_API int lsf_detect_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int src_h, int src_w, size_t pitch,
+                             int mem_kind, lsf_segments *out);
+
+/* Replaces: BinaryDescriptor::compute (binary_descriptor_custom.cpp:524-687) on the frames of the last
+ * lsf_detect_batch / lsf_front_end_batch call (still resident on the device): segs->lines_px,
+ * segs->frame_offset (n_frames+1) in -> segs->desc out. */
+LSF_API int lsf_describe_batch(lsf_ctx *ctx, lsf_segments *segs);
+
+/* Replaces: GroundProjectionNode.lineseglist_cb + LineSanityNode.processSegmentList for S segments:
+ * pixels_normalized f32 [S][4], color u8 [S]  ->  ground f64 [S][4], keep u8 [S].  Host or device per mem_kind. */
+LSF_API int lsf_project_filter_batch(lsf_ctx *ctx, const float *pixels_normalized, const uint8_t *color, int n_seg,
+                                     int mem_kind, double *ground, uint8_t *keep);
+
+/* Replaces: BinaryDescriptorMatcher::knnMatch(query, train, k) (binary_descriptor_matcher.cpp:258-335).
+ * Exact brute force over 32-byte codes; rows ascending by distance, ties by ascending train index;
+ * neighbours farther than max_dist (Mihasher D = 128; pass 256 for unbounded) are reported as -1. */
+LSF_API int lsf_knn_hamming(lsf_ctx *ctx, const uint8_t *query, int nq, const uint8_t *train, int nm, int k,
+                            int max_dist, int mem_kind, int32_t *idx, int32_t *dist);
+
+/* Map of accumulated line descriptors (BinaryDescriptorMatcher::add/train/clear,
+ * binary_descriptor_matcher.cpp:55-105).  The map is device resident. */
+LSF_API int lsf_map_clear(lsf_ctx *ctx);
+LSF_API int lsf_map_add(lsf_ctx *ctx, const uint8_t *desc, int n, int mem_kind);
+LSF_API int lsf_map_size(lsf_ctx *ctx);
+
+/* Parity taps: copy a dense stage map of frame `frame` of the last batch to host memory `dst`. */
+LSF_API int lsf_get_tap(lsf_ctx *ctx, int tap, int frame, void *dst, size_t dst_bytes);
+
+/* Processed-image geometry for an input of src_h x src_w: h = img_h - top_cutoff, w = img_w. */
+LSF_API int lsf_image_dims(const lsf_ctx *ctx, int *h, int *w, int *lsd_h, int *lsd_w);
+
+/* Device-time of the kernels of the last batch (ms, CUDA events on the ctx stream), by stage name.
+ * names/ms arrays of capacity cap; returns the number of entries. */
+LSF_API int lsf_last_timings(lsf_ctx *ctx, const char **names, float *ms, int cap);
+
+/* Number of kernels this library launched since ctx creation. */
+LSF_API long long lsf_launch_count(const lsf_ctx *ctx);
+
+/* The CUDA stream (cudaStream_t) the ctx launches on, for callers that time with their own events. */
+LSF_API void *lsf_stream(lsf_ctx *ctx);
+
+LSF_API const char *lsf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSF_H */

@@ -1,0 +1,154 @@
+// common.cuh -- shared declarations of the lsf CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/lsf.h"
+
+namespace lsf {
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+// ---- bit-plane indices -------------------------------------------------------------------------
+// planes A: written by the colour+Canny kernel
+enum { PA_RAW_W = 0, PA_RAW_Y = 1, PA_RAW_R = 2, PA_CAND = 3, PA_STRONG = 4, PA_COUNT = 5 };
+// planes B: written by the hysteresis/dilate kernel
+enum { PB_EDGE = 0, PB_BW0 = 1, PB_EC0 = 4, PB_COUNT = 7 };
+
+// ---- geometry of one batch ---------------------------------------------------------------------
+struct Dims {
+    int n;                 // frames
+    int src_h, src_w;      // input frame
+    size_t src_pitch;      // bytes per input row
+    size_t src_frame;      // bytes per input frame
+    int dh, dw, top;       // resize target (img_size) and top_cutoff
+    int h, w;              // processed image: h = dh - top, w = dw
+    int wp;                // 32-bit words per bit-plane row
+    int sh, sw, swp;       // LSD scaled image and its words per row
+    int pixcap;            // LSD support-pixel capacity per colour image
+    int segcap;            // segment capacity per colour image
+    int identity_geom;     // 1: no resize (dh==src_h, dw==src_w)
+    int identity_color;    // 1: AntiInstagram scale==1, shift==0
+};
+
+// one entry per 32 scaled pixels: defined-angle bits + number of defined pixels before this word
+struct LsdWord { u32 bits; u32 base; };
+
+// per LSD support pixel (raster order inside one colour image)
+struct LsdPix {
+    float ang_deg;  // fastAtan2 result in degrees
+    float c, s;     // cosf / sinf of float(angle_rad)
+    u32 g2;         // gx^2 + gy^2 (norm = sqrt(g2/4))
+};
+
+// parameters handed to kernels by value
+struct ColorParams {
+    int lo[4][3], hi[4][3];
+    int canny_lo, canny_hi;
+    float ai_scale[3], ai_shift[3];
+};
+
+struct CamParams {
+    double K[9], D[5], R[9], P[12], Hg[9];
+    int cam_w, cam_h;
+    double lanewidth, lw_white, lw_yellow, d_min, d_max, phi_min, phi_max;
+};
+
+// raw LSD output per accepted segment (before normals / ordering)
+struct LsdSeg { float x1, y1, x2, y2; };
+
+// ---- device buffers of a context ------------------------------------------------------------------
+struct Buffers {
+    u8 *src;            // staged input frames (when the caller passes host memory)
+    u32 *planesA;       // [n][PA_COUNT][h][wp]
+    u32 *planesB;       // [n][PB_COUNT][h][wp]
+    u8 *gray;           // [n][h][w]
+    short *dx, *dy;     // [n][h][w]  (descriptor path)
+    LsdWord *lsdw;      // [n*3][sh][swp]
+    LsdPix *pix;        // [n*3][pixcap]
+    u32 *pixxy;         // [n*3][pixcap]  (y<<16 | x)
+    u8 *used;           // [n*3][pixcap]
+    u32 *order;         // [n*3][pixcap]  seed order (compact indices)
+    u32 *reg;           // [n*3][pixcap]  region scratch
+    int *pixcount;      // [n*3]
+    u32 *g2max;         // [n*3]
+    LsdSeg *rawseg;     // [n*3][segcap]
+    int *segcount;      // [n*3]
+    int *frame_off;     // [n+1]
+    int *flags;         // [4] overflow flags: 0 pix overflow, 1 seg overflow, 2 out capacity
+    // compacted per-segment outputs (capacity outcap)
+    int outcap;
+    u8 *o_color; float *o_lines; double *o_normals; float *o_centers; float *o_pixn; float *o_nf32;
+    double *o_ground; u8 *o_keep; u8 *o_desc; int *o_frame; int *o_midx; int *o_mdist;
+};
+
+// ---- kernel launchers (one per .cu file) ------------------------------------------------------------
+struct TmaDesc { CUtensorMap map; int valid; };
+
+void launch_color_canny(const Dims &d, const ColorParams &cp, const u8 *src, const TmaDesc &tma, u32 *planesA, u8 *gray,
+                        cudaStream_t st);
+void launch_hysteresis(const Dims &d, int dilate, const u32 *planesA, u32 *planesB, cudaStream_t st);
+void launch_lsd_pre(const Dims &d, const u32 *planesB, Buffers &b, cudaStream_t st);
+void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st);
+void launch_segments(const Dims &d, const CamParams &cam, Buffers &b, int do_ground, cudaStream_t st);
+void launch_gray_sobel(const Dims &d, const u8 *gray, short *dx, short *dy, cudaStream_t st);
+void launch_lbd(const Dims &d, const float *lines, const int *frame_of_seg, int nseg_cap, const int *nseg_dev,
+                const short *dx, const short *dy, u8 *desc, cudaStream_t st);
+void launch_project_filter(const CamParams &cam, const float *pixn, const u8 *color, int nseg, double *ground, u8 *keep,
+                           cudaStream_t st);
+void launch_knn(const u8 *q, int nq_cap, const int *nq_dev, const u8 *m, int nm, int k, int max_dist, int *idx, int *dist,
+                void *scratch, size_t scratch_bytes, cudaStream_t st);
+size_t knn_scratch_bytes(int nq, int nm, int k);
+void launch_unpack_plane(const u32 *plane, int h, int w, int wp, u8 *dst, cudaStream_t st);
+void launch_labels_tap(const u32 *planesA_frame, int h, int w, int wp, u8 *dst, cudaStream_t st);
+void launch_image_tap(const Dims &d, const ColorParams &cp, const u8 *src_frame, u8 *dst, cudaStream_t st);
+
+extern long long g_launches;  // kernels launched by this library
+
+// ---- small device helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// nearest-resize source index: min(floor(d * src/dst), src-1)  (cv2.resize INTER_NEAREST)
+__device__ __forceinline__ int nearest_src(int d, int src, int dst)
+{
+    if (src == dst) return d;
+    int s = (int)floor((double)d * ((double)src / (double)dst));
+    return s > src - 1 ? src - 1 : s;
+}
+
+// AntiInstagram scale/shift (float32) followed by cv2.convertScaleAbs: sat_u8(rint(|v*scale + shift|))
+__device__ __forceinline__ u8 color_correct(u8 v, float sc, float sf)
+{
+    float t = __fadd_rn(__fmul_rn((float)v, sc), sf);
+    int r = __float2int_rn(fabsf(t));
+    return (u8)(r > 255 ? 255 : r);
+}
+
+// OpenCV fastAtan2 (degrees), float32 polynomial without FMA contraction
+__device__ __forceinline__ float fast_atan2_deg(float y, float x)
+{
+    const float k = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * k, p3 = -0.3258083974640975f * k;
+    const float p5 = 0.1555786518463281f * k, p7 = -0.04432655554792128f * k;
+    const float eps = 2.2204460492503131e-16f;
+    float ax = fabsf(x), ay = fabsf(y), a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+}  // namespace lsf

@@ -1,0 +1,192 @@
+// k_segments.cu -- K10+K12: per-segment epilogue, one thread per segment, fused in one pass:
+//   normals + endpoint ordering      line_detector_lsd.py:74-125 (_findNormal, _checkBounds, _correctPixelOrdering)
+//   normalisation + float32 wire     line_detector_node.py:194-205, 251-265 (Vector2D.msg float32)
+//   ground projection                GroundProjection.py:38-48 (vector2pixel), :64-78 (pixel2ground), SURVEY.md A.7
+//   line_sanity filter               line_sanity_node.py:48-117
+// plus the scan that turns per-(frame,colour) counts into the frame-ordered output layout
+// (white, yellow, red; LSD order inside a colour: line_detector_node.py:197-205).
+#include "common.cuh"
+
+namespace lsf {
+
+// ---- exclusive scan of segcount[n*3] -> imgoff[n*3], frame_off[n+1] (single block) ----
+__global__ void __launch_bounds__(1024) k_seg_offsets(int nimg, const int *__restrict__ segcount, int *__restrict__ imgoff,
+                                                     int *__restrict__ frame_off, int outcap, int *__restrict__ flags)
+{
+    __shared__ int wtot[32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nimg; base += 1024) {
+        int i = base + tid;
+        int v = i < nimg ? segcount[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wtot[warp] = incl;
+        __syncthreads();
+        int woff = 0;
+        for (int k = 0; k < warp; ++k) woff += wtot[k];
+        int excl = carry + woff + incl - v;
+        if (i < nimg) {
+            imgoff[i] = excl;
+            if (i % 3 == 0) frame_off[i / 3] = excl;
+        }
+        __syncthreads();
+        if (tid == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        frame_off[nimg / 3] = carry;
+        if (carry > outcap) atomicMax(&flags[2], carry);
+    }
+}
+
+// ---- ground projection + sanity (float64, as numpy / cv2.undistortPoints) ----
+__device__ __forceinline__ void undistort_point(const CamParams &cam, double u, double v, double &ou, double &ov)
+{
+    const double fx = cam.K[0], fy = cam.K[4], cx = cam.K[2], cy = cam.K[5];
+    const double k1 = cam.D[0], k2 = cam.D[1], p1 = cam.D[2], p2 = cam.D[3], k3 = cam.D[4];
+    double x = (u - cx) / fx, y = (v - cy) / fy;
+    const double x0 = x, y0 = y;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        double r2 = x * x + y * y;
+        double icdist = 1.0 / (1 + ((k3 * r2 + k2) * r2 + k1) * r2);
+        double dX = 2 * p1 * x * y + p2 * (r2 + 2 * x * x);
+        double dY = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y;
+        x = (x0 - dX) * icdist;
+        y = (y0 - dY) * icdist;
+    }
+    double xx = cam.R[0] * x + cam.R[1] * y + cam.R[2], yy = cam.R[3] * x + cam.R[4] * y + cam.R[5];
+    double ww = 1. / (cam.R[6] * x + cam.R[7] * y + cam.R[8]);
+    x = xx * ww; y = yy * ww;
+    ou = x * cam.P[0] + cam.P[2];
+    ov = y * cam.P[5] + cam.P[6];
+}
+
+__device__ __forceinline__ void vec2ground(const CamParams &cam, float vx, float vy, double &gx, double &gy)
+{
+    double u = cam.cam_w * (double)vx, v = cam.cam_h * (double)vy;
+    if (u < 0) u = 0;
+    if (u > cam.cam_w - 1) u = cam.cam_w - 1;
+    if (v < 0) v = 0;
+    if (v > cam.cam_h - 1) v = 0;  // sic: GroundProjection.py:47
+    double ru, rv;
+    undistort_point(cam, u, v, ru, rv);
+    const double *H = cam.Hg;
+    double g0 = H[0] * ru + H[1] * rv + H[2], g1 = H[3] * ru + H[4] * rv + H[5], g2 = H[6] * ru + H[7] * rv + H[8];
+    gx = g0 / g2; gy = g1 / g2;
+}
+
+__device__ __forceinline__ u8 sanity_keep(const CamParams &cam, double p1x, double p1y, double p2x, double p2y, int colour)
+{
+    if (p1x < 0 || p2x < 0) return 0;
+    if (colour != LSF_WHITE && colour != LSF_YELLOW) return 0;
+    double dx = p2x - p1x, dy = p2y - p1y, nrm = sqrt(dx * dx + dy * dy);
+    double tx = dx / nrm, ty = dy / nrm, nx = -ty, ny = tx;
+    double d1 = nx * p1x + ny * p1y, d2 = nx * p2x + ny * p2y;
+    double d_i = (d1 + d2) / 2, phi_i = asin(ty);
+    if (colour == LSF_WHITE) {
+        if (p1x > p2x) d_i = d_i - cam.lw_white;
+        else { d_i = -d_i; phi_i = -phi_i; }
+        d_i = d_i - cam.lanewidth / 2;
+    } else {
+        if (p2x > p1x) { d_i = d_i - cam.lw_yellow; phi_i = -phi_i; }
+        else d_i = -d_i;
+        d_i = cam.lanewidth / 2 - d_i;
+    }
+    if (d_i > cam.d_max || d_i < cam.d_min || phi_i < cam.phi_min || phi_i > cam.phi_max) return 0;
+    return 1;
+}
+
+__global__ void __launch_bounds__(128) k_segments(Dims d, CamParams cam, int do_ground, const LsdSeg *__restrict__ rawseg,
+                                                 const int *__restrict__ segcount, const int *__restrict__ imgoff,
+                                                 const u32 *__restrict__ planesB, int outcap, u8 *__restrict__ o_color,
+                                                 float *__restrict__ o_lines, double *__restrict__ o_normals,
+                                                 float *__restrict__ o_centers, float *__restrict__ o_pixn,
+                                                 float *__restrict__ o_nf32, double *__restrict__ o_ground,
+                                                 u8 *__restrict__ o_keep, int *__restrict__ o_frame)
+{
+    const int img = blockIdx.y, f = img / 3, c = img - f * 3;
+    const int cnt = segcount[img];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    const int o = imgoff[img] + i;
+    if (o >= outcap) return;
+    LsdSeg s = rawseg[(size_t)img * d.segcap + i];
+    float x1 = s.x1, y1 = s.y1, x2 = s.x2, y2 = s.y2;
+    // float32 numpy arithmetic (no FMA): length, unit normal candidates, centre
+    float ddx = x1 - x2, ddy = y1 - y2;
+    float len = sqrtf(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)));
+    float dx = __fdiv_rn(y2 - y1, len), dy = __fdiv_rn(x1 - x2, len);
+    float cx = __fdiv_rn(x1 + x2, 2.f), cy = __fdiv_rn(y1 + y2, 2.f);
+    int x3 = clampi((int)__fsub_rn(cx, __fmul_rn(3.f, dx)), 0, d.w - 1), y3 = clampi((int)__fsub_rn(cy, __fmul_rn(3.f, dy)), 0, d.h - 1);
+    int x4 = clampi((int)__fadd_rn(cx, __fmul_rn(3.f, dx)), 0, d.w - 1), y4 = clampi((int)__fadd_rn(cy, __fmul_rn(3.f, dy)), 0, d.h - 1);
+    const u32 *bw = planesB + ((size_t)f * PB_COUNT + PB_BW0 + c) * (size_t)d.h * d.wp;
+    int b3 = (bw[(size_t)y3 * d.wp + (x3 >> 5)] >> (x3 & 31)) & 1, b4 = (bw[(size_t)y4 * d.wp + (x4 >> 5)] >> (x4 & 31)) & 1;
+    int sign = (b3 && !b4) ? 1 : -1;
+    double nx = (double)dx * (double)sign, ny = (double)dy * (double)sign;
+    double flag = __dsub_rn(__dmul_rn((double)(x2 - x1), ny), __dmul_rn((double)(y2 - y1), nx));
+    if (flag > 0) { float t = x1; x1 = x2; x2 = t; t = y1; y1 = y2; y2 = t; }
+    o_color[o] = (u8)c;
+    o_frame[o] = f;
+    reinterpret_cast<float4 *>(o_lines)[o] = make_float4(x1, y1, x2, y2);
+    reinterpret_cast<double2 *>(o_normals)[o] = make_double2(nx, ny);
+    reinterpret_cast<float2 *>(o_centers)[o] = make_float2(cx, cy);
+    reinterpret_cast<float2 *>(o_nf32)[o] = make_float2((float)nx, (float)ny);
+    // (lines + [0, cut, 0, cut]) * [1/W, 1/H, 1/W, 1/H] in float64, stored as float32 (Vector2D)
+    double rw = 1.0 / (double)d.dw, rh = 1.0 / (double)d.dh, cut = (double)d.top;
+    float p0 = (float)__dmul_rn((double)x1, rw), p1 = (float)__dmul_rn(__dadd_rn((double)y1, cut), rh);
+    float p2 = (float)__dmul_rn((double)x2, rw), p3 = (float)__dmul_rn(__dadd_rn((double)y2, cut), rh);
+    reinterpret_cast<float4 *>(o_pixn)[o] = make_float4(p0, p1, p2, p3);
+    if (do_ground) {
+        double g[4];
+        vec2ground(cam, p0, p1, g[0], g[1]);
+        vec2ground(cam, p2, p3, g[2], g[3]);
+        reinterpret_cast<double2 *>(o_ground)[2 * o] = make_double2(g[0], g[1]);
+        reinterpret_cast<double2 *>(o_ground)[2 * o + 1] = make_double2(g[2], g[3]);
+        o_keep[o] = sanity_keep(cam, g[0], g[1], g[2], g[3], c);
+    }
+}
+
+void launch_segments(const Dims &d, const CamParams &cam, Buffers &b, int do_ground, cudaStream_t st)
+{
+    // imgoff lives in the tail of frame_off's allocation: frame_off[n+1], imgoff[n*3]
+    int *imgoff = b.frame_off + (d.n + 1);
+    k_seg_offsets<<<1, 1024, 0, st>>>(d.n * 3, b.segcount, imgoff, b.frame_off, b.outcap, b.flags);
+    ++g_launches;
+    dim3 grid((d.segcap + 127) / 128, d.n * 3);
+    k_segments<<<grid, 128, 0, st>>>(d, cam, do_ground, b.rawseg, b.segcount, imgoff, b.planesB, b.outcap, b.o_color, b.o_lines,
+                                     b.o_normals, b.o_centers, b.o_pixn, b.o_nf32, b.o_ground, b.o_keep, b.o_frame);
+    ++g_launches;
+}
+
+// ---- standalone ground projection + sanity over S segments (lsf_project_filter_batch) ----
+__global__ void k_project_filter(CamParams cam, const float *__restrict__ pixn, const u8 *__restrict__ color, int nseg,
+                                 double *__restrict__ ground, u8 *__restrict__ keep)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nseg) return;
+    float4 p = reinterpret_cast<const float4 *>(pixn)[i];
+    double g[4];
+    vec2ground(cam, p.x, p.y, g[0], g[1]);
+    vec2ground(cam, p.z, p.w, g[2], g[3]);
+    ground[4 * (size_t)i] = g[0]; ground[4 * (size_t)i + 1] = g[1];
+    ground[4 * (size_t)i + 2] = g[2]; ground[4 * (size_t)i + 3] = g[3];
+    keep[i] = sanity_keep(cam, g[0], g[1], g[2], g[3], color[i]);
+}
+
+void launch_project_filter(const CamParams &cam, const float *pixn, const u8 *color, int nseg, double *ground, u8 *keep,
+                           cudaStream_t st)
+{
+    if (nseg <= 0) return;
+    k_project_filter<<<(nseg + 127) / 128, 128, 0, st>>>(cam, pixn, color, nseg, ground, keep);
+    ++g_launches;
+}
+
+}  // namespace lsf

@@ -1,0 +1,614 @@
+// lsf_api.cu -- the C ABI (include/lsf.h): context, device scratch, batch pipeline, copies.
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace lsf {
+long long g_launches = 0;
+}
+using namespace lsf;
+
+static std::string g_create_error;
+
+struct StageTime { const char *name; cudaEvent_t ev; };
+
+struct lsf_ctx {
+    lsf_config cfg;
+    int device;
+    cudaStream_t st;
+    Buffers b;
+    Dims d;            // geometry of the last batch
+    ColorParams cp;
+    CamParams cam;
+    int max_batch, max_src_h, max_src_w;
+    int h, w, wp, sh, sw, swp, pixcap, segcap;
+    bool have_batch;
+    const u8 *last_src;   // device pointer of the last batch's frames
+    // map of descriptors
+    u8 *map;
+    int map_n, map_cap;
+    void *knn_scratch;
+    size_t knn_scratch_cap;
+    // pinned host staging
+    int *h_small;         // [n*3 + n+1 + 4]
+    u8 *tap_tmp;
+    size_t tap_cap;
+    u8 *seg_in;           // staging for describe/project inputs given in host memory
+    size_t seg_in_cap;
+    // TMA
+    TmaDesc tma;
+    const u8 *tma_src; int tma_n, tma_h, tma_w; size_t tma_pitch;
+    // timing
+    std::vector<StageTime> events;
+    int n_events;
+    long long launches0;
+    std::string err;
+};
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            char buf_[512];                                                                            \
+            snprintf(buf_, sizeof(buf_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            ctx->err = buf_;                                                                           \
+            return LSF_E_CUDA;                                                                         \
+        }                                                                                              \
+    } while (0)
+
+static int fail(lsf_ctx *ctx, int code, const std::string &msg)
+{
+    if (ctx) ctx->err = msg; else g_create_error = msg;
+    return code;
+}
+
+// ---- defaults (the reference's YAML files) --------------------------------------------------------------
+extern "C" int lsf_default_config(lsf_config *c)
+{
+    if (!c) return LSF_E_ARG;
+    memset(c, 0, sizeof(*c));
+    c->img_h = 120; c->img_w = 160; c->top_cutoff = 40;  // line_detector_node/default.yaml:1-2
+    const int lo[4][3] = {{0, 0, 150}, {25, 140, 100}, {0, 140, 100}, {165, 140, 100}};
+    const int hi[4][3] = {{180, 60, 255}, {45, 255, 255}, {15, 255, 255}, {180, 255, 255}};
+    memcpy(c->hsv_lo, lo, sizeof(lo)); memcpy(c->hsv_hi, hi, sizeof(hi));
+    c->dilation_kernel_size = 3; c->canny_lo = 80; c->canny_hi = 200;
+    for (int i = 0; i < 3; ++i) { c->ai_scale[i] = 1.f; c->ai_shift[i] = 0.f; }
+    const double K[9] = {307.7379294605756, 0, 329.692367951685, 0, 314.9827773443905, 244.4605588877848, 0, 0, 1};
+    const double D[5] = {-0.2565888993516047, 0.04481160508242147, -0.00505275149956019, 0.001308569367976665, 0};
+    const double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    const double P[12] = {210.1107940673828, 0, 327.2577820024981, 0, 0, 253.8408660888672, 239.9969353923052, 0, 0, 0, 1, 0};
+    const double Hg[9] = {-4.89775e-05, -0.0002150858, -0.1818273, 0.00099274, 1.202336e-06, -0.3280241,
+                          -0.0004281805, -0.007185673, 1};
+    memcpy(c->K, K, sizeof(K)); memcpy(c->D, D, sizeof(D)); memcpy(c->R, R, sizeof(R)); memcpy(c->P, P, sizeof(P));
+    memcpy(c->Hgnd, Hg, sizeof(Hg));
+    c->cam_w = 640; c->cam_h = 480;
+    c->lanewidth = 0.23; c->linewidth_white = 0.05; c->linewidth_yellow = 0.025;
+    c->d_min = -0.15; c->d_max = 0.3; c->phi_min = -1.5; c->phi_max = 1.5;
+    c->max_batch = 1; c->max_src_h = 480; c->max_src_w = 640;
+    return LSF_OK;
+}
+
+template <typename T>
+static cudaError_t dalloc(T **p, size_t count)
+{
+    return cudaMalloc((void **)p, (count ? count : 1) * sizeof(T));
+}
+
+extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
+{
+    if (!cfg || !out) return fail(nullptr, LSF_E_ARG, "lsf_create: null argument");
+    *out = nullptr;
+    if (cfg->img_h < 16 || cfg->img_w < 16 || cfg->top_cutoff < 0 || cfg->img_h - cfg->top_cutoff < 8)
+        return fail(nullptr, LSF_E_CONFIG, "lsf_create: img_size / top_cutoff out of range (need >= 16x16 and >= 8 rows after the cut)");
+    if (cfg->img_w > 32768 || cfg->img_h > 32768) return fail(nullptr, LSF_E_CONFIG, "lsf_create: img_size too large (max 32768)");
+    if (cfg->dilation_kernel_size != 3 && cfg->dilation_kernel_size != 1)
+        return fail(nullptr, LSF_E_CONFIG, "lsf_create: dilation_kernel_size must be 3 (cross) or 1; other ellipse sizes are not implemented");
+    if (cfg->canny_lo > cfg->canny_hi) return fail(nullptr, LSF_E_CONFIG, "lsf_create: canny_thresholds must be [low, high]");
+    if (cfg->cam_w <= 0 || cfg->cam_h <= 0) return fail(nullptr, LSF_E_CONFIG, "lsf_create: camera size missing");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, LSF_E_CUDA, "lsf_create: no CUDA device (this library has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, LSF_E_CONFIG, "lsf_create: bad device ordinal");
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, cfg->device);
+    if (prop.major != 10) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "lsf_create: device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+        return fail(nullptr, LSF_E_CUDA, buf);
+    }
+    lsf_ctx *ctx = new lsf_ctx();
+    ctx->cfg = *cfg;
+    ctx->device = cfg->device;
+    ctx->have_batch = false;
+    ctx->map = nullptr; ctx->map_n = 0; ctx->map_cap = 0;
+    ctx->knn_scratch = nullptr; ctx->knn_scratch_cap = 0;
+    ctx->tap_tmp = nullptr; ctx->tap_cap = 0;
+    ctx->seg_in = nullptr; ctx->seg_in_cap = 0;
+    ctx->tma.valid = 0; ctx->tma_src = nullptr;
+    ctx->n_events = 0;
+    memset(&ctx->b, 0, sizeof(ctx->b));
+    auto bail = [&](int code, const std::string &msg) { g_create_error = msg; lsf_destroy(ctx); return code; };
+#define CKC(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return bail(LSF_E_CUDA, std::string(#call " failed: ") + cudaGetErrorString(e_)); \
+    } while (0)
+    CKC(cudaSetDevice(ctx->device));
+    CKC(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
+    ctx->max_batch = cfg->max_batch > 0 ? cfg->max_batch : 1;
+    ctx->max_src_h = cfg->max_src_h > 0 ? cfg->max_src_h : cfg->img_h;
+    ctx->max_src_w = cfg->max_src_w > 0 ? cfg->max_src_w : cfg->img_w;
+    ctx->h = cfg->img_h - cfg->top_cutoff; ctx->w = cfg->img_w;
+    ctx->wp = (ctx->w + 31) / 32;
+    ctx->sw = (int)lrint(ctx->w * 0.8); ctx->sh = (int)lrint(ctx->h * 0.8);
+    ctx->swp = (ctx->sw + 31) / 32;
+    const size_t Np = (size_t)ctx->sh * ctx->sw;
+    ctx->pixcap = cfg->max_pixels_per_color > 0 ? cfg->max_pixels_per_color : (int)std::max<size_t>(4096, Np / 4);
+    if ((size_t)ctx->pixcap > Np) ctx->pixcap = (int)Np;
+    ctx->segcap = cfg->max_segments_per_color > 0 ? cfg->max_segments_per_color
+                                                  : (int)std::max<size_t>(512, (size_t)ctx->h * ctx->w / 256);
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 3; ++j) { ctx->cp.lo[i][j] = cfg->hsv_lo[i][j]; ctx->cp.hi[i][j] = cfg->hsv_hi[i][j]; }
+    ctx->cp.canny_lo = cfg->canny_lo; ctx->cp.canny_hi = cfg->canny_hi;
+    for (int i = 0; i < 3; ++i) { ctx->cp.ai_scale[i] = cfg->ai_scale[i]; ctx->cp.ai_shift[i] = cfg->ai_shift[i]; }
+    memcpy(ctx->cam.K, cfg->K, sizeof(cfg->K)); memcpy(ctx->cam.D, cfg->D, sizeof(cfg->D));
+    memcpy(ctx->cam.R, cfg->R, sizeof(cfg->R)); memcpy(ctx->cam.P, cfg->P, sizeof(cfg->P));
+    memcpy(ctx->cam.Hg, cfg->Hgnd, sizeof(cfg->Hgnd));
+    ctx->cam.cam_w = cfg->cam_w; ctx->cam.cam_h = cfg->cam_h;
+    ctx->cam.lanewidth = cfg->lanewidth; ctx->cam.lw_white = cfg->linewidth_white; ctx->cam.lw_yellow = cfg->linewidth_yellow;
+    ctx->cam.d_min = cfg->d_min; ctx->cam.d_max = cfg->d_max; ctx->cam.phi_min = cfg->phi_min; ctx->cam.phi_max = cfg->phi_max;
+
+    const size_t n = ctx->max_batch, N = (size_t)ctx->h * ctx->w, ps = (size_t)ctx->h * ctx->wp;
+    Buffers &b = ctx->b;
+    CKC(dalloc(&b.src, n * ctx->max_src_h * ctx->max_src_w * 3));
+    CKC(dalloc(&b.planesA, n * PA_COUNT * ps));
+    CKC(dalloc(&b.planesB, n * PB_COUNT * ps));
+    CKC(dalloc(&b.gray, n * N));
+    CKC(dalloc(&b.dx, n * N * 2));
+    b.dy = nullptr;
+    CKC(dalloc(&b.lsdw, n * 3 * (size_t)ctx->sh * ctx->swp));
+    CKC(dalloc(&b.pix, n * 3 * ctx->pixcap));
+    CKC(dalloc(&b.pixxy, n * 3 * ctx->pixcap));
+    CKC(dalloc(&b.used, n * 3 * ctx->pixcap));
+    CKC(dalloc(&b.order, n * 3 * ctx->pixcap));
+    CKC(dalloc(&b.reg, n * 3 * ctx->pixcap));
+    CKC(dalloc(&b.pixcount, n * 3));
+    CKC(dalloc(&b.g2max, n * 3));
+    CKC(dalloc(&b.rawseg, n * 3 * ctx->segcap));
+    CKC(dalloc(&b.segcount, n * 3));
+    CKC(dalloc(&b.frame_off, (n + 1) + n * 3));
+    CKC(dalloc(&b.flags, 4));
+    b.outcap = (int)std::min<size_t>(n * 3 * ctx->segcap, (size_t)1 << 30);
+    const size_t oc = b.outcap;
+    CKC(dalloc(&b.o_color, oc)); CKC(dalloc(&b.o_lines, oc * 4)); CKC(dalloc(&b.o_normals, oc * 2));
+    CKC(dalloc(&b.o_centers, oc * 2)); CKC(dalloc(&b.o_pixn, oc * 4)); CKC(dalloc(&b.o_nf32, oc * 2));
+    CKC(dalloc(&b.o_ground, oc * 4)); CKC(dalloc(&b.o_keep, oc)); CKC(dalloc(&b.o_desc, oc * 32));
+    CKC(dalloc(&b.o_frame, oc));
+    b.o_midx = nullptr; b.o_mdist = nullptr;
+    CKC(cudaMallocHost((void **)&ctx->h_small, (n * 3 + n + 1 + 4) * sizeof(int)));
+    CKC(cudaMemsetAsync(b.flags, 0, 4 * sizeof(int), ctx->st));
+    CKC(cudaStreamSynchronize(ctx->st));
+    ctx->launches0 = g_launches;
+    *out = ctx;
+    return LSF_OK;
+#undef CKC
+}
+
+extern "C" void lsf_destroy(lsf_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    Buffers &b = ctx->b;
+    void *ptrs[] = {b.src, b.planesA, b.planesB, b.gray, b.dx, b.lsdw, b.pix, b.pixxy, b.used, b.order, b.reg, b.pixcount,
+                    b.g2max, b.rawseg, b.segcount, b.frame_off, b.flags, b.o_color, b.o_lines, b.o_normals, b.o_centers,
+                    b.o_pixn, b.o_nf32, b.o_ground, b.o_keep, b.o_desc, b.o_frame, b.o_midx, b.o_mdist, ctx->map,
+                    ctx->knn_scratch, ctx->tap_tmp, ctx->seg_in};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (ctx->h_small) cudaFreeHost(ctx->h_small);
+    for (auto &e : ctx->events) cudaEventDestroy(e.ev);
+    if (ctx->st) cudaStreamDestroy(ctx->st);
+    delete ctx;
+}
+
+extern "C" const char *lsf_last_error(const lsf_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int lsf_set_color_transform(lsf_ctx *ctx, const float scale[3], const float shift[3])
+{
+    if (!ctx || !scale || !shift) return LSF_E_ARG;
+    for (int i = 0; i < 3; ++i) { ctx->cfg.ai_scale[i] = scale[i]; ctx->cfg.ai_shift[i] = shift[i]; }
+    return LSF_OK;
+}
+
+extern "C" int lsf_image_dims(const lsf_ctx *ctx, int *h, int *w, int *lsd_h, int *lsd_w)
+{
+    if (!ctx) return LSF_E_ARG;
+    if (h) *h = ctx->h;
+    if (w) *w = ctx->w;
+    if (lsd_h) *lsd_h = ctx->sh;
+    if (lsd_w) *lsd_w = ctx->sw;
+    return LSF_OK;
+}
+
+// ---- TMA descriptor for the input frames: [frame][row][byte] uint8, box 208 x 36 x 1 ---------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static void make_tma(lsf_ctx *ctx, const u8 *src, int n, int sh, int sw, size_t pitch)
+{
+    if (ctx->tma.valid && ctx->tma_src == src && ctx->tma_n == n && ctx->tma_h == sh && ctx->tma_w == sw && ctx->tma_pitch == pitch) return;
+    ctx->tma.valid = 0;
+    if (sw < 128 || sh < 40 || (pitch % 16) != 0 || (((uintptr_t)src) % 16) != 0 || ((pitch * sh) % 16) != 0) return;
+    static PFN_encodeTiled enc = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            enc = (PFN_encodeTiled)fn;
+    }
+    if (!enc) return;
+    cuuint64_t gdim[3] = {(cuuint64_t)sw * 3, (cuuint64_t)sh, (cuuint64_t)n};
+    cuuint64_t gstr[2] = {(cuuint64_t)pitch, (cuuint64_t)pitch * sh};
+    cuuint32_t box[3] = {208, 36, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&ctx->tma.map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)src, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return;
+    ctx->tma.valid = 1;
+    ctx->tma_src = src; ctx->tma_n = n; ctx->tma_h = sh; ctx->tma_w = sw; ctx->tma_pitch = pitch;
+}
+
+static void mark(lsf_ctx *ctx, const char *name)
+{
+    if (ctx->n_events == (int)ctx->events.size()) {
+        StageTime s; s.name = name;
+        cudaEventCreate(&s.ev);
+        ctx->events.push_back(s);
+    }
+    ctx->events[ctx->n_events].name = name;
+    cudaEventRecord(ctx->events[ctx->n_events].ev, ctx->st);
+    ++ctx->n_events;
+}
+
+extern "C" int lsf_last_timings(lsf_ctx *ctx, const char **names, float *ms, int cap)
+{
+    if (!ctx) return 0;
+    int n = 0;
+    for (int i = 0; i + 1 < ctx->n_events && n < cap; ++i) {
+        float t = 0;
+        cudaEventElapsedTime(&t, ctx->events[i].ev, ctx->events[i + 1].ev);
+        names[n] = ctx->events[i + 1].name;
+        ms[n] = t;
+        ++n;
+    }
+    return n;
+}
+
+extern "C" long long lsf_launch_count(const lsf_ctx *ctx) { return ctx ? g_launches - ctx->launches0 : g_launches; }
+extern "C" void *lsf_stream(lsf_ctx *ctx) { return ctx ? (void *)ctx->st : nullptr; }
+extern "C" const char *lsf_version(void) { return "lsf 0.1 (sm_100a)"; }
+
+static cudaMemcpyKind out_kind(int mem) { return mem == LSF_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost; }
+
+static int ensure_knn(lsf_ctx *ctx, int nq, int nm, int k)
+{
+    size_t need = knn_scratch_bytes(nq, nm, k);
+    if (need > ctx->knn_scratch_cap) {
+        if (ctx->knn_scratch) cudaFree(ctx->knn_scratch);
+        ctx->knn_scratch = nullptr; ctx->knn_scratch_cap = 0;
+        CK(cudaMalloc(&ctx->knn_scratch, need));
+        ctx->knn_scratch_cap = need;
+    }
+    return LSF_OK;
+}
+
+// ---- the batch pipeline ---------------------------------------------------------------------------------------
+extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int src_h, int src_w, size_t pitch, int mem_kind,
+                                   int stages, int k, lsf_segments *out)
+{
+    if (!ctx) return LSF_E_ARG;
+    if (!bgr || !out || n <= 0) return fail(ctx, LSF_E_ARG, "lsf_front_end_batch: null frames / output or n <= 0");
+    if (n > ctx->max_batch) return fail(ctx, LSF_E_CAPACITY, "lsf_front_end_batch: n exceeds max_batch " + std::to_string(ctx->max_batch));
+    if (src_h <= 0 || src_w <= 0 || src_h > ctx->max_src_h || src_w > ctx->max_src_w)
+        return fail(ctx, LSF_E_CAPACITY, "lsf_front_end_batch: frame larger than max_src_h x max_src_w");
+    if (pitch < (size_t)src_w * 3) return fail(ctx, LSF_E_ARG, "lsf_front_end_batch: pitch smaller than a row");
+    if (!(stages & LSF_STAGE_DETECT)) return fail(ctx, LSF_E_ARG, "lsf_front_end_batch: stages must include LSF_STAGE_DETECT");
+    if ((stages & LSF_STAGE_MATCH) && !(stages & LSF_STAGE_DESCRIBE))
+        return fail(ctx, LSF_E_ARG, "lsf_front_end_batch: LSF_STAGE_MATCH needs LSF_STAGE_DESCRIBE");
+    if ((stages & LSF_STAGE_MATCH) && (k < 1 || k > 8)) return fail(ctx, LSF_E_ARG, "lsf_front_end_batch: k must be 1..8");
+    CK(cudaSetDevice(ctx->device));
+    Buffers &b = ctx->b;
+    Dims d;
+    d.n = n; d.src_h = src_h; d.src_w = src_w;
+    d.dh = ctx->cfg.img_h; d.dw = ctx->cfg.img_w; d.top = ctx->cfg.top_cutoff;
+    d.h = ctx->h; d.w = ctx->w; d.wp = ctx->wp; d.sh = ctx->sh; d.sw = ctx->sw; d.swp = ctx->swp;
+    d.pixcap = ctx->pixcap; d.segcap = ctx->segcap;
+    d.identity_geom = (d.dh == src_h && d.dw == src_w);
+    for (int i = 0; i < 3; ++i) { ctx->cp.ai_scale[i] = ctx->cfg.ai_scale[i]; ctx->cp.ai_shift[i] = ctx->cfg.ai_shift[i]; }
+    d.identity_color = 1;
+    for (int i = 0; i < 3; ++i) if (ctx->cp.ai_scale[i] != 1.f || ctx->cp.ai_shift[i] != 0.f) d.identity_color = 0;
+
+    ctx->n_events = 0;
+    mark(ctx, "start");
+    const u8 *src;
+    if (mem_kind == LSF_MEM_DEVICE) {
+        src = bgr; d.src_pitch = pitch; d.src_frame = pitch * src_h;
+    } else {
+        d.src_pitch = (size_t)src_w * 3; d.src_frame = d.src_pitch * src_h;
+        CK(cudaMemcpy2DAsync(b.src, d.src_pitch, bgr, pitch, (size_t)src_w * 3, (size_t)src_h * n, cudaMemcpyHostToDevice, ctx->st));
+        src = b.src;
+        mark(ctx, "h2d");
+    }
+    ctx->last_src = src; ctx->d = d; ctx->have_batch = true;
+    if (d.identity_geom) make_tma(ctx, src, n, src_h, src_w, d.src_pitch); else ctx->tma.valid = 0;
+
+    CK(cudaMemsetAsync(b.flags, 0, 4 * sizeof(int), ctx->st));
+    launch_color_canny(d, ctx->cp, src, ctx->tma, b.planesA, b.gray, ctx->st);
+    mark(ctx, "color_canny");
+    launch_hysteresis(d, ctx->cfg.dilation_kernel_size, b.planesA, b.planesB, ctx->st);
+    mark(ctx, "hysteresis_dilate");
+    launch_lsd_pre(d, b.planesB, b, ctx->st);
+    mark(ctx, "lsd_pre");
+    launch_lsd_core(d, b, ctx->st);
+    mark(ctx, "lsd_core");
+    launch_segments(d, ctx->cam, b, (stages & LSF_STAGE_GROUND) ? 1 : 0, ctx->st);
+    mark(ctx, "segments");
+    if (stages & LSF_STAGE_DESCRIBE) {
+        launch_gray_sobel(d, b.gray, b.dx, nullptr, ctx->st);
+        mark(ctx, "gray_sobel");
+        launch_lbd(d, b.o_lines, b.o_frame, b.outcap, b.frame_off + n, b.dx, nullptr, b.o_desc, ctx->st);
+        mark(ctx, "lbd");
+    }
+    // small results first: counts, offsets, flags
+    int *hs = ctx->h_small;
+    CK(cudaMemcpyAsync(hs, b.segcount, (size_t)n * 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(hs + n * 3, b.frame_off, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(hs + n * 3 + n + 1, b.flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaGetLastError());
+    const int *flags = hs + n * 3 + n + 1;
+    if (flags[0]) return fail(ctx, LSF_E_CAPACITY, "LSD support pixels of one colour image = " + std::to_string(flags[0]) +
+                                                       " exceed max_pixels_per_color = " + std::to_string(ctx->pixcap));
+    if (flags[1]) return fail(ctx, LSF_E_CAPACITY, "segments of one colour image = " + std::to_string(flags[1]) +
+                                                       " exceed max_segments_per_color = " + std::to_string(ctx->segcap));
+    const int S = hs[n * 3 + n];
+    out->n_frames = n; out->n_segments = S;
+    if (S > out->capacity) return fail(ctx, LSF_E_CAPACITY, "lsf_segments.capacity too small: need " + std::to_string(S));
+
+    // matching against the ctx map (needs S on the host only for the grid size; queries are device resident)
+    if ((stages & LSF_STAGE_MATCH) && S > 0) {
+        if (ctx->map_n <= 0) return fail(ctx, LSF_E_ARG, "LSF_STAGE_MATCH: the map is empty (lsf_map_add first)");
+        int rc = ensure_knn(ctx, S, ctx->map_n, k);
+        if (rc) return rc;
+        if (!b.o_midx) { CK(dalloc(&b.o_midx, (size_t)b.outcap * 8)); CK(dalloc(&b.o_mdist, (size_t)b.outcap * 8)); }
+        launch_knn(b.o_desc, S, nullptr, ctx->map, ctx->map_n, k, 256, b.o_midx, b.o_mdist, ctx->knn_scratch, ctx->knn_scratch_cap, ctx->st);
+        mark(ctx, "knn");
+    }
+    const cudaMemcpyKind kind = out_kind(out->mem);
+    if (out->counts) {
+        if (out->mem == LSF_MEM_DEVICE) CK(cudaMemcpyAsync(out->counts, b.segcount, (size_t)n * 3 * sizeof(int), kind, ctx->st));
+        else memcpy(out->counts, hs, (size_t)n * 3 * sizeof(int));
+    }
+    if (out->frame_offset) {
+        if (out->mem == LSF_MEM_DEVICE) CK(cudaMemcpyAsync(out->frame_offset, b.frame_off, (size_t)(n + 1) * sizeof(int), kind, ctx->st));
+        else memcpy(out->frame_offset, hs + n * 3, (size_t)(n + 1) * sizeof(int));
+    }
+    if (S > 0) {
+        const size_t s = S;
+#define COPY(dst, srcp, bytes) do { if (dst) CK(cudaMemcpyAsync(dst, srcp, (bytes), kind, ctx->st)); } while (0)
+        COPY(out->color, b.o_color, s);
+        COPY(out->lines_px, b.o_lines, s * 16);
+        COPY(out->normals, b.o_normals, s * 16);
+        COPY(out->centers, b.o_centers, s * 8);
+        COPY(out->pixels_normalized, b.o_pixn, s * 16);
+        COPY(out->normal_f32, b.o_nf32, s * 8);
+        if (stages & LSF_STAGE_GROUND) { COPY(out->ground, b.o_ground, s * 32); COPY(out->keep, b.o_keep, s); }
+        if (stages & LSF_STAGE_DESCRIBE) COPY(out->desc, b.o_desc, s * 32);
+        if (stages & LSF_STAGE_MATCH) { COPY(out->match_idx, b.o_midx, s * k * 4); COPY(out->match_dist, b.o_mdist, s * k * 4); }
+#undef COPY
+    }
+    mark(ctx, "d2h");
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaGetLastError());
+    return LSF_OK;
+}
+
+extern "C" int lsf_detect_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int src_h, int src_w, size_t pitch, int mem_kind,
+                                lsf_segments *out)
+{
+    return lsf_front_end_batch(ctx, bgr, n, src_h, src_w, pitch, mem_kind, LSF_STAGE_DETECT, 0, out);
+}
+
+static int stage_in(lsf_ctx *ctx, size_t bytes)
+{
+    if (bytes > ctx->seg_in_cap) {
+        if (ctx->seg_in) cudaFree(ctx->seg_in);
+        ctx->seg_in = nullptr; ctx->seg_in_cap = 0;
+        CK(cudaMalloc((void **)&ctx->seg_in, bytes));
+        ctx->seg_in_cap = bytes;
+    }
+    return LSF_OK;
+}
+
+extern "C" int lsf_describe_batch(lsf_ctx *ctx, lsf_segments *segs)
+{
+    if (!ctx || !segs) return LSF_E_ARG;
+    if (!ctx->have_batch) return fail(ctx, LSF_E_ARG, "lsf_describe_batch: no frames resident (call lsf_detect_batch first)");
+    if (!segs->lines_px || !segs->frame_offset || !segs->desc) return fail(ctx, LSF_E_ARG, "lsf_describe_batch: lines_px, frame_offset and desc are required");
+    if (segs->n_frames != ctx->d.n) return fail(ctx, LSF_E_ARG, "lsf_describe_batch: n_frames differs from the resident batch");
+    CK(cudaSetDevice(ctx->device));
+    const int S = segs->n_segments, n = ctx->d.n;
+    if (S <= 0) return LSF_OK;
+    // layout of the staging buffer: lines f32[S][4] | frame_of_seg i32[S] | nseg i32 | desc u8[S][32]
+    size_t off_frame = (size_t)S * 16, off_n = off_frame + (size_t)S * 4, off_desc = (off_n + 4 + 15) & ~(size_t)15;
+    int rc = stage_in(ctx, off_desc + (size_t)S * 32);
+    if (rc) return rc;
+    std::vector<int> fo(n + 1);
+    if (segs->mem == LSF_MEM_DEVICE) {
+        CK(cudaMemcpy(fo.data(), segs->frame_offset, (n + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpyAsync(ctx->seg_in, segs->lines_px, (size_t)S * 16, cudaMemcpyDeviceToDevice, ctx->st));
+    } else {
+        memcpy(fo.data(), segs->frame_offset, (n + 1) * sizeof(int));
+        CK(cudaMemcpyAsync(ctx->seg_in, segs->lines_px, (size_t)S * 16, cudaMemcpyHostToDevice, ctx->st));
+    }
+    if (fo[n] != S) return fail(ctx, LSF_E_ARG, "lsf_describe_batch: frame_offset[n_frames] != n_segments");
+    std::vector<int> fos(S + 1);
+    for (int f = 0; f < n; ++f) {
+        if (fo[f] > fo[f + 1] || fo[f] < 0) return fail(ctx, LSF_E_ARG, "lsf_describe_batch: frame_offset not monotone");
+        for (int i = fo[f]; i < fo[f + 1]; ++i) fos[i] = f;
+    }
+    fos[S] = S;
+    CK(cudaMemcpyAsync(ctx->seg_in + off_frame, fos.data(), (size_t)(S + 1) * 4, cudaMemcpyHostToDevice, ctx->st));
+    launch_gray_sobel(ctx->d, ctx->b.gray, ctx->b.dx, nullptr, ctx->st);
+    launch_lbd(ctx->d, (const float *)ctx->seg_in, (const int *)(ctx->seg_in + off_frame), S, (const int *)(ctx->seg_in + off_n),
+               ctx->b.dx, nullptr, ctx->seg_in + off_desc, ctx->st);
+    CK(cudaMemcpyAsync(segs->desc, ctx->seg_in + off_desc, (size_t)S * 32, out_kind(segs->mem), ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaGetLastError());
+    return LSF_OK;
+}
+
+extern "C" int lsf_project_filter_batch(lsf_ctx *ctx, const float *pixn, const uint8_t *color, int n_seg, int mem_kind,
+                                        double *ground, uint8_t *keep)
+{
+    if (!ctx) return LSF_E_ARG;
+    if (n_seg < 0 || (n_seg > 0 && (!pixn || !color || !ground || !keep))) return fail(ctx, LSF_E_ARG, "lsf_project_filter_batch: null argument");
+    if (n_seg == 0) return LSF_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t S = n_seg;
+    if (mem_kind == LSF_MEM_DEVICE) {
+        launch_project_filter(ctx->cam, pixn, color, n_seg, ground, keep, ctx->st);
+    } else {
+        size_t off_col = S * 16, off_g = (off_col + S + 15) & ~(size_t)15, off_k = off_g + S * 32;
+        int rc = stage_in(ctx, off_k + S);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(ctx->seg_in, pixn, S * 16, cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaMemcpyAsync(ctx->seg_in + off_col, color, S, cudaMemcpyHostToDevice, ctx->st));
+        launch_project_filter(ctx->cam, (const float *)ctx->seg_in, ctx->seg_in + off_col, n_seg, (double *)(ctx->seg_in + off_g),
+                              ctx->seg_in + off_k, ctx->st);
+        CK(cudaMemcpyAsync(ground, ctx->seg_in + off_g, S * 32, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(keep, ctx->seg_in + off_k, S, cudaMemcpyDeviceToHost, ctx->st));
+    }
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaGetLastError());
+    return LSF_OK;
+}
+
+extern "C" int lsf_knn_hamming(lsf_ctx *ctx, const uint8_t *query, int nq, const uint8_t *train, int nm, int k, int max_dist,
+                               int mem_kind, int32_t *idx, int32_t *dist)
+{
+    if (!ctx) return LSF_E_ARG;
+    if (nq < 0 || nm < 0 || k < 1 || k > 8) return fail(ctx, LSF_E_ARG, "lsf_knn_hamming: bad sizes (k must be 1..8)");
+    if (nq == 0) return LSF_OK;
+    if (!query || !idx || !dist || (nm > 0 && !train)) return fail(ctx, LSF_E_ARG, "lsf_knn_hamming: null argument");
+    CK(cudaSetDevice(ctx->device));
+    ctx->n_events = 0;
+    const size_t Q = nq, M = nm;
+    const u8 *dq, *dm; int *di, *dd;
+    if (mem_kind == LSF_MEM_DEVICE) {
+        dq = query; dm = train; di = idx; dd = dist;
+    } else {
+        size_t off_m = Q * 32, off_i = off_m + M * 32, off_d = off_i + Q * k * 4;
+        int rc = stage_in(ctx, off_d + Q * k * 4);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(ctx->seg_in, query, Q * 32, cudaMemcpyHostToDevice, ctx->st));
+        if (M) CK(cudaMemcpyAsync(ctx->seg_in + off_m, train, M * 32, cudaMemcpyHostToDevice, ctx->st));
+        dq = ctx->seg_in; dm = ctx->seg_in + off_m; di = (int *)(ctx->seg_in + off_i); dd = (int *)(ctx->seg_in + off_d);
+    }
+    int rc = ensure_knn(ctx, nq, nm > 0 ? nm : 1, k);
+    if (rc) return rc;
+    mark(ctx, "start");
+    launch_knn(dq, nq, nullptr, dm, nm, k, max_dist, di, dd, ctx->knn_scratch, ctx->knn_scratch_cap, ctx->st);
+    mark(ctx, "knn");
+    if (mem_kind != LSF_MEM_DEVICE) {
+        CK(cudaMemcpyAsync(idx, di, Q * k * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(dist, dd, Q * k * 4, cudaMemcpyDeviceToHost, ctx->st));
+    }
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaGetLastError());
+    return LSF_OK;
+}
+
+extern "C" int lsf_map_clear(lsf_ctx *ctx)
+{
+    if (!ctx) return LSF_E_ARG;
+    ctx->map_n = 0;
+    return LSF_OK;
+}
+
+extern "C" int lsf_map_size(lsf_ctx *ctx) { return ctx ? ctx->map_n : LSF_E_ARG; }
+
+extern "C" int lsf_map_add(lsf_ctx *ctx, const uint8_t *desc, int n, int mem_kind)
+{
+    if (!ctx || n < 0 || (n > 0 && !desc)) return LSF_E_ARG;
+    if (n == 0) return LSF_OK;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->map_n + n > ctx->map_cap) {
+        int ncap = std::max(ctx->map_cap * 2, ctx->map_n + n);
+        ncap = std::max(ncap, 4096);
+        u8 *nm = nullptr;
+        CK(cudaMalloc((void **)&nm, (size_t)ncap * 32));
+        if (ctx->map_n) CK(cudaMemcpyAsync(nm, ctx->map, (size_t)ctx->map_n * 32, cudaMemcpyDeviceToDevice, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        if (ctx->map) cudaFree(ctx->map);
+        ctx->map = nm; ctx->map_cap = ncap;
+    }
+    CK(cudaMemcpyAsync(ctx->map + (size_t)ctx->map_n * 32, desc, (size_t)n * 32,
+                       mem_kind == LSF_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->map_n += n;
+    return LSF_OK;
+}
+
+// ---- parity taps --------------------------------------------------------------------------------------------
+extern "C" int lsf_get_tap(lsf_ctx *ctx, int tap, int frame, void *dst, size_t dst_bytes)
+{
+    if (!ctx || !dst) return LSF_E_ARG;
+    if (!ctx->have_batch) return fail(ctx, LSF_E_ARG, "lsf_get_tap: no batch processed yet");
+    const Dims &d = ctx->d;
+    if (frame < 0 || frame >= d.n) return fail(ctx, LSF_E_ARG, "lsf_get_tap: frame out of range");
+    CK(cudaSetDevice(ctx->device));
+    const size_t N = (size_t)d.h * d.w, ps = (size_t)d.h * d.wp;
+    size_t need = tap == LSF_TAP_IMAGE ? N * 3 : (tap == LSF_TAP_DX || tap == LSF_TAP_DY) ? N * 2 : N;
+    if (dst_bytes < need) return fail(ctx, LSF_E_CAPACITY, "lsf_get_tap: need " + std::to_string(need) + " bytes");
+    if (need > ctx->tap_cap) {
+        if (ctx->tap_tmp) cudaFree(ctx->tap_tmp);
+        ctx->tap_tmp = nullptr; ctx->tap_cap = 0;
+        CK(cudaMalloc((void **)&ctx->tap_tmp, N * 4));
+        ctx->tap_cap = N * 4;
+    }
+    const u32 *pa = ctx->b.planesA + (size_t)frame * PA_COUNT * ps;
+    const u32 *pb = ctx->b.planesB + (size_t)frame * PB_COUNT * ps;
+    const void *srcp = ctx->tap_tmp;
+    switch (tap) {
+    case LSF_TAP_IMAGE: launch_image_tap(d, ctx->cp, ctx->last_src + (size_t)frame * d.src_frame, ctx->tap_tmp, ctx->st); break;
+    case LSF_TAP_LABELS: launch_labels_tap(pa, d.h, d.w, d.wp, ctx->tap_tmp, ctx->st); break;
+    case LSF_TAP_EDGES: launch_unpack_plane(pb + PB_EDGE * ps, d.h, d.w, d.wp, ctx->tap_tmp, ctx->st); break;
+    case LSF_TAP_BW_WHITE: case LSF_TAP_BW_YELLOW: case LSF_TAP_BW_RED:
+        launch_unpack_plane(pb + (PB_BW0 + tap - LSF_TAP_BW_WHITE) * ps, d.h, d.w, d.wp, ctx->tap_tmp, ctx->st); break;
+    case LSF_TAP_EC_WHITE: case LSF_TAP_EC_YELLOW: case LSF_TAP_EC_RED:
+        launch_unpack_plane(pb + (PB_EC0 + tap - LSF_TAP_EC_WHITE) * ps, d.h, d.w, d.wp, ctx->tap_tmp, ctx->st); break;
+    case LSF_TAP_GRAY: srcp = ctx->b.gray + (size_t)frame * N; break;
+    case LSF_TAP_DX: case LSF_TAP_DY: {
+        // de-interleave on the host
+        std::vector<short> tmp(N * 2);
+        CK(cudaMemcpyAsync(tmp.data(), ctx->b.dx + (size_t)frame * N * 2, N * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        short *o = (short *)dst;
+        for (size_t i = 0; i < N; ++i) o[i] = tmp[2 * i + (tap == LSF_TAP_DY ? 1 : 0)];
+        return LSF_OK;
+    }
+    default: return fail(ctx, LSF_E_ARG, "lsf_get_tap: unknown tap");
+    }
+    CK(cudaMemcpyAsync(dst, srcp, need, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaGetLastError());
+    return LSF_OK;
+}
