@@ -74,7 +74,7 @@ struct Buffers {
     u32 *pixxy;         // [n*3][pixcap]  (y<<16 | x)
     u8 *used;           // [n*3][pixcap]
     u32 *order;         // [n*3][pixcap]  seed order (compact indices)
-    u32 *reg;           // [n*3][pixcap]  region scratch
+    u32 *reg;           // [n*3][2*pixcap] region point list + scratch
     int *pixcount;      // [n*3]
     u32 *g2max;         // [n*3]
     LsdSeg *rawseg;     // [n*3][segcap]

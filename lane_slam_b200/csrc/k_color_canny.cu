@@ -15,7 +15,8 @@
 namespace lsf {
 
 constexpr int TW = 64, TH = 32, HALO = 2;
-constexpr int BOX_X = 208;               // bytes per tile row: (64+4)*3 = 204, padded to a multiple of 16
+constexpr int XOFF = 16;                 // bytes of left padding: TMA needs a 16-byte aligned inner start (measured)
+constexpr int BOX_X = 224;               // bytes per tile row: 16 + (64+2)*3 = 214, padded to a multiple of 16
 constexpr int BOX_Y = TH + 2 * HALO;     // 36
 constexpr int MAGW = TW + 4;             // 68: (TW+2) columns + pad
 constexpr int NT = 256;
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(NT) k_color_canny(const __grid_constant__ CUte
         if (tid == 0) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(BOX_X * BOX_Y)
                          : "memory");
-            int c0 = tx0 * 3 - HALO * 3, c1 = ty0 - HALO + d.top, c2 = f;
+            int c0 = tx0 * 3 - XOFF, c1 = ty0 - HALO + d.top, c2 = f;
             asm volatile(
                 "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                 ::"r"(smem_u32(tile)), "l"(&tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar_a)
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(NT) k_color_canny(const __grid_constant__ CUte
         const u8 *fsrc = src + (size_t)f * d.src_frame;
         for (int i = tid; i < BOX_Y * BOX_X; i += NT) {
             int r = i / BOX_X, k = i - r * BOX_X;
-            int yy = ty0 - HALO + r, xb = tx0 * 3 - HALO * 3 + k;
+            int yy = ty0 - HALO + r, xb = tx0 * 3 - XOFF + k;
             u8 v = 0;
             if (yy >= 0 && yy < d.h && xb >= 0 && xb < d.w * 3) {
                 int px = xb / 3, c = xb - px * 3;
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(NT) k_color_canny(const __grid_constant__ CUte
     if (!d.identity_color) {
         if (USE_TMA) __syncthreads();
         for (int i = tid; i < BOX_Y * BOX_X; i += NT) {
-            int c = (i % BOX_X) % 3;  // tile row starts at byte 3*(tx0-2): channel = k mod 3
+            int c = ((i % BOX_X) + 2) % 3;  // tile row starts at byte 3*tx0 - 16: channel = (k - 16) mod 3
             tile[i] = color_correct(tile[i], cp.ai_scale[c], cp.ai_shift[c]);
         }
         __syncthreads();
@@ -116,8 +117,7 @@ __global__ void __launch_bounds__(NT) k_color_canny(const __grid_constant__ CUte
             // BORDER_REPLICATE: clamp neighbour coordinates to the image, then address the tile
             int rm = (max(iy - 1, 0) - (ty0 - HALO)) * BOX_X, r0 = (iy - (ty0 - HALO)) * BOX_X,
                 rp = (min(iy + 1, d.h - 1) - (ty0 - HALO)) * BOX_X;
-            int cm = (max(ix - 1, 0) - (tx0 - HALO)) * 3, c0 = (ix - (tx0 - HALO)) * 3,
-                cq = (min(ix + 1, d.w - 1) - (tx0 - HALO)) * 3;
+            int cm = (max(ix - 1, 0) - tx0) * 3 + XOFF, c0 = (ix - tx0) * 3 + XOFF, cq = (min(ix + 1, d.w - 1) - tx0) * 3 + XOFF;
             best = -1;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(NT) k_color_canny(const __grid_constant__ CUte
                 cand = ismax;
                 strong = ismax && c > cp.canny_hi;
             }
-            const u8 *px = tile + (ty + HALO) * BOX_X + (tx + HALO) * 3;
+            const u8 *px = tile + (ty + HALO) * BOX_X + tx * 3 + XOFF;
             int b = px[0], g = px[1], r = px[2];
             int v = max(b, max(g, r)), mn = min(b, min(g, r)), diff = v - mn;
             int s = (diff * s_sdiv[v] + 2048) >> 12;

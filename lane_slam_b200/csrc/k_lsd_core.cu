@@ -29,7 +29,7 @@ struct Img {
     const u32 *xy;
     u8 *used;
     u32 *reg;
-    int W, H, swp, n;
+    int W, H, swp, n, cap;
     double logNT;
 };
 
@@ -184,36 +184,59 @@ __device__ int grow(const Img &im, int seed, double prec, double &reg_angle_out)
     return nreg;
 }
 
+// ---- reference-order accumulation --------------------------------------------------------------------
+// The reference adds region points one by one in double precision; rounding (and through it theta, the
+// rectangle corners and finally the NFA pixel counts) depends on that order.  Lanes compute the per-point
+// terms in parallel, park them in shared memory, and every lane then adds them in point order.
+struct Seq3 { double a[32], b[32], c[32]; };
+
+__device__ __forceinline__ void seq_add3(Seq3 &sm, int cnt, double ta, double tb, double tc, double &A, double &B, double &C)
+{
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    sm.a[lane] = ta; sm.b[lane] = tb; sm.c[lane] = tc;
+    __syncwarp();
+    for (int j = 0; j < cnt; ++j) { A += sm.a[j]; B += sm.b[j]; C += sm.c[j]; }
+}
+
 // ---- rectangle fit ------------------------------------------------------------------------------------
-__device__ void region2rect(const Img &im, int nreg, double reg_angle, double prec, double p, Rect &r)
+__device__ void region2rect(const Img &im, Seq3 &sm, int nreg, double reg_angle, double prec, double p, Rect &r)
 {
     const int lane = threadIdx.x & 31;
     double x = 0, y = 0, sum = 0;
-    for (int i = lane; i < nreg; i += 32) {
-        u32 q = im.reg[i];
-        u32 xy = im.xy[q];
-        double w = sqrt((double)im.pix[q].g2 / 4.0);
-        x += (double)(xy & 0xffffu) * w;
-        y += (double)(xy >> 16) * w;
-        sum += w;
+    for (int i0 = 0; i0 < nreg; i0 += 32) {
+        int i = i0 + lane;
+        double tx = 0, ty = 0, tw = 0;
+        if (i < nreg) {
+            u32 q = im.reg[i];
+            u32 xy = im.xy[q];
+            tw = sqrt((double)im.pix[q].g2 / 4.0);
+            tx = (double)(xy & 0xffffu) * tw;
+            ty = (double)(xy >> 16) * tw;
+        }
+        seq_add3(sm, min(32, nreg - i0), tx, ty, tw, x, y, sum);
     }
-    x = wsum(x); y = wsum(y); sum = wsum(sum);
     x /= sum; y /= sum;
     double Ixx = 0, Iyy = 0, Ixy = 0;
-    for (int i = lane; i < nreg; i += 32) {
-        u32 q = im.reg[i];
-        u32 xy = im.xy[q];
-        double w = sqrt((double)im.pix[q].g2 / 4.0);
-        double dx = (double)(xy & 0xffffu) - x, dy = (double)(xy >> 16) - y;
-        Ixx += dy * dy * w; Iyy += dx * dx * w; Ixy -= dx * dy * w;
+    for (int i0 = 0; i0 < nreg; i0 += 32) {
+        int i = i0 + lane;
+        double ta = 0, tb = 0, tc = 0;
+        if (i < nreg) {
+            u32 q = im.reg[i];
+            u32 xy = im.xy[q];
+            double w = sqrt((double)im.pix[q].g2 / 4.0);
+            double dx = (double)(xy & 0xffffu) - x, dy = (double)(xy >> 16) - y;
+            ta = dy * dy * w; tb = dx * dx * w; tc = -(dx * dy * w);   // Ixy -= dx*dy*w
+        }
+        seq_add3(sm, min(32, nreg - i0), ta, tb, tc, Ixx, Iyy, Ixy);
     }
-    Ixx = wsum(Ixx); Iyy = wsum(Iyy); Ixy = wsum(Ixy);
     double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
     double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_deg((float)(lambda - Ixx), (float)Ixy)
                                            : (double)fast_atan2_deg((float)Ixy, (float)(lambda - Iyy));
     theta *= kDEG2RAD;
     if (fabs(angle_diff_signed(theta, reg_angle)) > prec) theta += kPI;
     double dx = cos(theta), dy = sin(theta);
+    // extents: min / max are order independent
     double lmin = 0, lmax = 0, wmn = 0, wmx = 0;
     for (int i = lane; i < nreg; i += 32) {
         u32 xy = im.xy[im.reg[i]];
@@ -235,7 +258,7 @@ __device__ __forceinline__ double rect_density(int nreg, const Rect &r)
 }
 
 // ---- density refinement (refine + reduce_region_radius) ------------------------------------------------
-__device__ bool refine(const Img &im, int &nreg, double &reg_angle, double prec, double p, Rect &rec)
+__device__ bool refine(const Img &im, Seq3 &sm, int &nreg, double &reg_angle, double prec, double p, Rect &rec)
 {
     const double density_th = 0.7;
     const int lane = threadIdx.x & 31;
@@ -245,23 +268,27 @@ __device__ bool refine(const Img &im, int &nreg, double &reg_angle, double prec,
     const double xc = (double)(sxy & 0xffffu), yc = (double)(sxy >> 16);
     const double ang_c = (double)im.pix[seed].ang_deg * kDEG2RAD;
     double sum = 0, s_sum = 0, cnt = 0;
-    for (int i = lane; i < nreg; i += 32) {
-        u32 q = im.reg[i];
-        im.used[q] = 0;
-        u32 xy = im.xy[q];
-        double ex = (double)(xy & 0xffffu) - xc, ey = (double)(xy >> 16) - yc;
-        if (sqrt(ex * ex + ey * ey) < rec.width) {
-            double ad = angle_diff_signed((double)im.pix[q].ang_deg * kDEG2RAD, ang_c);
-            sum += ad; s_sum += ad * ad; cnt += 1.0;
+    for (int i0 = 0; i0 < nreg; i0 += 32) {
+        int i = i0 + lane;
+        double ta = 0, tb = 0, tc = 0;
+        if (i < nreg) {
+            u32 q = im.reg[i];
+            im.used[q] = 0;
+            u32 xy = im.xy[q];
+            double ex = (double)(xy & 0xffffu) - xc, ey = (double)(xy >> 16) - yc;
+            if (sqrt(ex * ex + ey * ey) < rec.width) {
+                double ad = angle_diff_signed((double)im.pix[q].ang_deg * kDEG2RAD, ang_c);
+                ta = ad; tb = ad * ad; tc = 1.0;
+            }
         }
+        seq_add3(sm, min(32, nreg - i0), ta, tb, tc, sum, s_sum, cnt);
     }
-    sum = wsum(sum); s_sum = wsum(s_sum); cnt = wsum(cnt);
     __syncwarp();
     double mean = sum / cnt;
     double tau = 2.0 * sqrt((s_sum - 2.0 * mean * sum) / cnt + mean * mean);
     nreg = grow(im, seed, tau, reg_angle);
     if (nreg < 2) return false;
-    region2rect(im, nreg, reg_angle, prec, p, rec);
+    region2rect(im, sm, nreg, reg_angle, prec, p, rec);
     double density = rect_density(nreg, rec);
     if (density < density_th) {
         double r1 = (xc - rec.x1) * (xc - rec.x1) + (yc - rec.y1) * (yc - rec.y1);
@@ -269,8 +296,26 @@ __device__ bool refine(const Img &im, int &nreg, double &reg_angle, double prec,
         double radSq = r1 > r2 ? r1 : r2;
         while (density < density_th) {
             radSq *= 0.75 * 0.75;
-            // drop points farther than the radius (order-preserving warp compaction; the seed stays first)
-            int nout = 0;
+            // Drop points farther than the radius exactly like the reference's swap-with-last loop
+            // (reg[i] <- reg[last], pop, re-test i): kept points before position K stay in place and the
+            // j-th hole (ascending) receives the j-th kept point counted from the back.  The order matters
+            // because the following rectangle sums are accumulated in region order.
+            u32 *scratch = im.reg + im.cap;
+            int K = 0;
+            for (int i0 = 0; i0 < nreg; i0 += 32) {
+                int i = i0 + lane;
+                bool keep = false;
+                if (i < nreg) {
+                    u32 q = im.reg[i];
+                    u32 xy = im.xy[q];
+                    double ex = xc - (double)(xy & 0xffffu), ey = yc - (double)(xy >> 16);
+                    keep = !(ex * ex + ey * ey > radSq);
+                    if (!keep) im.used[q] = 0;
+                }
+                K += __popc(__ballot_sync(FULL, keep));
+            }
+            // fillers: kept points at positions >= K, ranked from the back
+            int before = 0;   // kept points in [0, i0)
             for (int i0 = 0; i0 < nreg; i0 += 32) {
                 int i = i0 + lane;
                 u32 q = 0;
@@ -280,17 +325,33 @@ __device__ bool refine(const Img &im, int &nreg, double &reg_angle, double prec,
                     u32 xy = im.xy[q];
                     double ex = xc - (double)(xy & 0xffffu), ey = yc - (double)(xy >> 16);
                     keep = !(ex * ex + ey * ey > radSq);
-                    if (!keep) im.used[q] = 0;
                 }
                 u32 m = __ballot_sync(FULL, keep);
-                __syncwarp();
-                if (keep) im.reg[nout + __popc(m & ((1u << lane) - 1u))] = q;
-                nout += __popc(m);
-                __syncwarp();
+                int incl = before + __popc(m & ((2u << lane) - 1u));
+                if (keep && i >= K) scratch[K - incl] = q;          // kept points after i = K - incl
+                before += __popc(m);
             }
+            __syncwarp();
+            before = 0;
+            for (int i0 = 0; i0 < K; i0 += 32) {
+                int i = i0 + lane;
+                bool keep = true;
+                if (i < K) {
+                    u32 xy = im.xy[im.reg[i]];
+                    double ex = xc - (double)(xy & 0xffffu), ey = yc - (double)(xy >> 16);
+                    keep = !(ex * ex + ey * ey > radSq);
+                }
+                u32 m = __ballot_sync(FULL, keep);
+                int excl = before + __popc(m & ((1u << lane) - 1u));  // kept points in [0, i)
+                __syncwarp();
+                if (i < K && !keep) im.reg[i] = scratch[i - excl];   // hole rank = holes before i
+                before += __popc(m);
+            }
+            __syncwarp();
+            int nout = K;
             nreg = nout;
             if (nreg < 2) return false;
-            region2rect(im, nreg, reg_angle, prec, p, rec);
+            region2rect(im, sm, nreg, reg_angle, prec, p, rec);
             density = rect_density(nreg, rec);
         }
     }
@@ -424,6 +485,7 @@ __global__ void __launch_bounds__(32) k_lsd_core(Dims d, const LsdWord *__restri
                                                 int *__restrict__ segcount, int *__restrict__ flags)
 {
     __shared__ u32 hist[1024];
+    __shared__ Seq3 sm;
     const int img = blockIdx.x, lane = threadIdx.x;
     Img im;
     im.n = pixcount[img];
@@ -432,7 +494,8 @@ __global__ void __launch_bounds__(32) k_lsd_core(Dims d, const LsdWord *__restri
     im.pix = pix + (size_t)img * d.pixcap;
     im.xy = pixxy + (size_t)img * d.pixcap;
     im.used = used + (size_t)img * d.pixcap;
-    im.reg = reg + (size_t)img * d.pixcap;
+    im.reg = reg + (size_t)img * 2 * d.pixcap;   // second half: scratch of reduce_region_radius
+    im.cap = d.pixcap;
     u32 *ord = order + (size_t)img * d.pixcap;
     const int n = im.n;
     if (n == 0) {
@@ -500,8 +563,8 @@ __global__ void __launch_bounds__(32) k_lsd_core(Dims d, const LsdWord *__restri
             int nreg = grow(im, seed, prec, reg_angle);
             if (nreg < min_reg) continue;
             Rect rec;
-            region2rect(im, nreg, reg_angle, prec, p, rec);
-            if (!refine(im, nreg, reg_angle, prec, p, rec)) continue;
+            region2rect(im, sm, nreg, reg_angle, prec, p, rec);
+            if (!refine(im, sm, nreg, reg_angle, prec, p, rec)) continue;
             double log_nfa = rect_improve(im, rec);
             if (!(log_nfa > 0.0)) continue;
             if (nout < d.segcap && lane == 0) {

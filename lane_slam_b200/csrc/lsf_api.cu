@@ -1,5 +1,6 @@
 // lsf_api.cu -- the C ABI (include/lsf.h): context, device scratch, batch pipeline, copies.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <string>
@@ -175,7 +176,7 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     CKC(dalloc(&b.pixxy, n * 3 * ctx->pixcap));
     CKC(dalloc(&b.used, n * 3 * ctx->pixcap));
     CKC(dalloc(&b.order, n * 3 * ctx->pixcap));
-    CKC(dalloc(&b.reg, n * 3 * ctx->pixcap));
+    CKC(dalloc(&b.reg, n * 3 * ctx->pixcap * 2));
     CKC(dalloc(&b.pixcount, n * 3));
     CKC(dalloc(&b.g2max, n * 3));
     CKC(dalloc(&b.rawseg, n * 3 * ctx->segcap));
@@ -233,7 +234,9 @@ extern "C" int lsf_image_dims(const lsf_ctx *ctx, int *h, int *w, int *lsd_h, in
     return LSF_OK;
 }
 
-// ---- TMA descriptor for the input frames: [frame][row][byte] uint8, box 208 x 36 x 1 ---------------------
+static bool g_debug_sync = getenv("LSF_DEBUG_SYNC") != nullptr;
+
+// ---- TMA descriptor for the input frames: [frame][row][byte] uint8, box 224 x 36 x 1 (inner start 16-byte aligned) ---------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -242,6 +245,7 @@ static void make_tma(lsf_ctx *ctx, const u8 *src, int n, int sh, int sw, size_t 
 {
     if (ctx->tma.valid && ctx->tma_src == src && ctx->tma_n == n && ctx->tma_h == sh && ctx->tma_w == sw && ctx->tma_pitch == pitch) return;
     ctx->tma.valid = 0;
+    if (getenv("LSF_NO_TMA")) return;
     if (sw < 128 || sh < 40 || (pitch % 16) != 0 || (((uintptr_t)src) % 16) != 0 || ((pitch * sh) % 16) != 0) return;
     static PFN_encodeTiled enc = nullptr;
     static bool tried = false;
@@ -256,10 +260,11 @@ static void make_tma(lsf_ctx *ctx, const u8 *src, int n, int sh, int sw, size_t 
     if (!enc) return;
     cuuint64_t gdim[3] = {(cuuint64_t)sw * 3, (cuuint64_t)sh, (cuuint64_t)n};
     cuuint64_t gstr[2] = {(cuuint64_t)pitch, (cuuint64_t)pitch * sh};
-    cuuint32_t box[3] = {208, 36, 1};
+    cuuint32_t box[3] = {224, 36, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&ctx->tma.map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)src, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (g_debug_sync) fprintf(stderr, "[lsf] cuTensorMapEncodeTiled -> %d\n", (int)r);
     if (r != CUDA_SUCCESS) return;
     ctx->tma.valid = 1;
     ctx->tma_src = src; ctx->tma_n = n; ctx->tma_h = sh; ctx->tma_w = sw; ctx->tma_pitch = pitch;
@@ -267,6 +272,11 @@ static void make_tma(lsf_ctx *ctx, const u8 *src, int n, int sh, int sw, size_t 
 
 static void mark(lsf_ctx *ctx, const char *name)
 {
+    if (g_debug_sync) {
+        cudaError_t e = cudaStreamSynchronize(ctx->st);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        fprintf(stderr, "[lsf] stage %-20s %s\n", name, e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+    }
     if (ctx->n_events == (int)ctx->events.size()) {
         StageTime s; s.name = name;
         cudaEventCreate(&s.ev);

@@ -1,0 +1,281 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI
+(lane_slam_b200 -> liblsf.so); the checker is the CPU oracle (oracle/), whose C model is pinned to
+cv2 4.13 / the reference in tests/test_oracle.py.
+
+Bars (BASELINE.json north_star):  colour labels, Canny map, segment counts (pre / post sanity), match
+indices: bit-exact;  endpoints <= 0.5 px (we assert exact and report the max error);  ground points
+<= 1e-4 m.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ENDPOINT_TOL_PX = 0.5      # north_star: segment endpoints within 0.5 px
+GROUND_TOL_M = 1e-4        # north_star: ground-projected points within 1e-4 m
+
+
+def _front_end(L, rg, isz, cut, H, W, n, **kw):
+    cam, Hg = (rg.DEFAULT_CAMERA, rg.DEFAULT_HOMOGRAPHY) if (W, H) == (640, 480) else rg.scaled_camera(W, H)
+    fe = L.FrontEnd(dict(L.DEFAULT_DETECTOR_CONFIGURATION), img_size=isz, top_cutoff=cut, camera=cam, homography=Hg,
+                    src_size=(H, W), max_batch=n, max_segments_per_frame=4096, **kw)
+    return fe, cam, Hg
+
+
+def _check_batch(L, cm, rg, cfg, frames, isz, cut, scale=(1, 1, 1), shift=(0, 0, 0), describe=True, dense_maps=True):
+    n, H, W = frames.shape[:3]
+    fe, cam, Hg = _front_end(L, rg, isz, cut, H, W, n, ai_scale=scale, ai_shift=shift)
+    stages = L.STAGE_DETECT | L.STAGE_GROUND | (L.STAGE_DESCRIBE if describe else 0)
+    b = fe.process(frames, stages=stages)
+    stats = dict(frames=n, exact_frames=0, max_endpoint_err=0.0, max_ground_err=0.0, desc_bits_bad=0, desc_bits=0)
+    for f in range(n):
+        o = cm.front_end_frame(frames[f], cfg, isz, cut, cam, Hg, scale, shift, descriptors=describe)
+        if dense_maps:
+            assert np.array_equal(fe.tap("image", f), o["image"]), "processed image differs (frame %d)" % f
+            lab = fe.tap("labels", f)
+            for c in range(3):
+                assert np.array_equal(((lab >> c) & 1).astype(bool), cm.color_mask(o["hsv"], cfg, c) > 0), \
+                    "colour label %d differs (frame %d)" % (c, f)
+            assert np.array_equal(lab >> 4, o["nms"]), "Canny NMS map differs (frame %d)" % f
+            assert np.array_equal(fe.tap("edges", f), o["edges"]), "Canny edges differ (frame %d)" % f
+            for i, c in enumerate(L.COLORS):
+                assert np.array_equal(fe.tap("bw_" + c, f), o["bw"][i]), "bw %s differs (frame %d)" % (c, f)
+                assert np.array_equal(fe.tap("ec_" + c, f), o["edge_color"][i]), "edge_color %s differs (frame %d)" % (c, f)
+        g = b.frame(f)
+        assert g["counts"] == o["counts"], "segment counts differ (frame %d): %s vs %s" % (f, g["counts"], o["counts"])
+        if len(o["lines_px"]):
+            err = float(np.abs(g["lines_px"] - o["lines_px"]).max())
+            stats["max_endpoint_err"] = max(stats["max_endpoint_err"], err)
+            assert err <= ENDPOINT_TOL_PX
+            assert np.array_equal(g["color"], o["color"])
+            gerr = float(np.abs(g["ground"] - o["ground"]).max())
+            stats["max_ground_err"] = max(stats["max_ground_err"], gerr)
+            assert gerr <= GROUND_TOL_M
+            assert np.array_equal(g["keep"], o["keep"]), "sanity keep mask differs (frame %d)" % f
+            exact = (np.array_equal(g["lines_px"], o["lines_px"]) and np.array_equal(g["normals"], o["normal64"])
+                     and np.array_equal(g["pixels_normalized"], o["pixels_normalized"]))
+            stats["exact_frames"] += bool(exact)
+            if describe:
+                assert np.array_equal(fe.tap("gray", f), o["gray"])
+                assert np.array_equal(fe.tap("dx", f), o["dx"]) and np.array_equal(fe.tap("dy", f), o["dy"])
+                stats["desc_bits_bad"] += int(np.unpackbits(g["desc"] ^ o["desc32"]).sum())
+                stats["desc_bits"] += g["desc"].size * 8
+        else:
+            stats["exact_frames"] += 1
+    fe.close()
+    return stats
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import lane_slam_b200 as L
+    from oracle import cmodel as cm, reference_glue as rg, synth
+    cfg = rg.check_configuration(dict(rg.DEFAULT_DETECTOR_CONFIG))
+    return L, cm, rg, synth, cfg
+
+
+def test_native_640x480(mods):
+    """configs[0]/[1] shape: 640x480, img_size native, top_cutoff 0."""
+    L, cm, rg, synth, cfg = mods
+    frames = np.stack([synth.frame(s) for s in range(24)])
+    st = _check_batch(L, cm, rg, cfg, frames, (480, 640), 0)
+    print(st)
+    assert st["exact_frames"] == st["frames"]
+    assert st["desc_bits_bad"] <= 1e-4 * st["desc_bits"]
+
+
+def test_reference_default_resize_crop(mods):
+    """The reference's own default: 640x480 -> nearest 160x120 -> top 40 rows cut (default.yaml:1-2)."""
+    L, cm, rg, synth, cfg = mods
+    frames = np.stack([synth.frame(s) for s in range(100, 124)])
+    st = _check_batch(L, cm, rg, cfg, frames, (120, 160), 40)
+    print(st)
+    assert st["exact_frames"] == st["frames"]
+
+
+def test_cutoff_and_color_transform(mods):
+    L, cm, rg, synth, cfg = mods
+    frames = np.stack([synth.frame(s) for s in range(200, 212)])
+    st = _check_batch(L, cm, rg, cfg, frames, (480, 640), 160, scale=(1.1, 0.93, 1.27), shift=(3.5, -7.25, 12.0))
+    print(st)
+    assert st["exact_frames"] == st["frames"]
+
+
+def test_sequence_frames(mods):
+    L, cm, rg, synth, cfg = mods
+    frames = synth.sequence(16, base_seed=7)
+    st = _check_batch(L, cm, rg, cfg, frames, (480, 640), 0)
+    print(st)
+    assert st["exact_frames"] == st["frames"]
+
+
+def test_dense_frames(mods):
+    """Dense-segment stress (C3-style content at 640x480): hundreds of segments per colour."""
+    L, cm, rg, synth, cfg = mods
+    frames = np.stack([synth.frame(s, dense=True) for s in range(6)])
+    st = _check_batch(L, cm, rg, cfg, frames, (480, 640), 0)
+    print(st)
+    assert st["exact_frames"] == st["frames"]
+
+
+def test_odd_sizes_and_ragged_words(mods):
+    """Widths that are not multiples of 32/64 (ragged bit-plane words, no TMA path)."""
+    L, cm, rg, synth, cfg = mods
+    for (H, W) in [(123, 161), (97, 203), (241, 321)]:
+        frames = np.stack([synth.frame(s, H, W) for s in range(4)])
+        st = _check_batch(L, cm, rg, cfg, frames, (H, W), 0)
+        assert st["exact_frames"] == st["frames"], (H, W, st)
+
+
+def test_1080p_dense_frame(mods):
+    """configs[2] shape (1920x1080 dense): multi-strip hysteresis, large support-pixel lists."""
+    L, cm, rg, synth, cfg = mods
+    frames = np.stack([synth.frame(s, 1080, 1920, dense=True) for s in range(2)])
+    st = _check_batch(L, cm, rg, cfg, frames, (1080, 1920), 0, describe=False)
+    print(st)
+    assert st["exact_frames"] == st["frames"]
+
+
+def test_empty_and_flat_frames(mods):
+    """No edges at all (flat frame) and pure noise: zero segments is success, not an error."""
+    L, cm, rg, synth, cfg = mods
+    flat = np.full((2, 480, 640, 3), 60, np.uint8)
+    rng = np.random.default_rng(1)
+    flat[1] = rng.integers(0, 256, (480, 640, 3), dtype=np.uint8)
+    st = _check_batch(L, cm, rg, cfg, flat, (480, 640), 0)
+    assert st["exact_frames"] == 2
+
+
+def test_plugin_class_matches_reference_contract(mods):
+    """LineDetectorB200 == LineDetectorLSD contract: dtypes, [] for empty colours, errors."""
+    L, cm, rg, synth, cfg = mods
+    det = L.LineDetectorB200(dict(L.DEFAULT_DETECTOR_CONFIGURATION))
+    ref = rg.LineDetectorLSD(dict(rg.DEFAULT_DETECTOR_CONFIG))
+    img = rg.preprocess(synth.frame(3), (120, 160), 40)
+    det.setImage(img); ref.setImage(img)
+    for color in L.COLORS:
+        a, r = det.detectLines(color), ref.detectLines(color)
+        assert np.array_equal(a.area, r.area)
+        if len(r.lines) == 0:
+            assert a.lines == [] and a.normals == [] and a.centers == []
+        else:
+            assert a.lines.dtype == np.float32 and a.normals.dtype == np.float64 and a.centers.dtype == np.float32
+            assert np.array_equal(a.lines, r.lines) and np.array_equal(a.normals, r.normals)
+            assert np.array_equal(a.centers, r.centers)
+    with pytest.raises(Exception):
+        det.detectLines('blue')
+    with pytest.raises(ValueError):
+        L.LineDetectorB200(dict(L.DEFAULT_DETECTOR_CONFIGURATION, bogus=1))
+    with pytest.raises(ValueError):
+        bad = dict(L.DEFAULT_DETECTOR_CONFIGURATION); bad.pop('hsv_red4')
+        L.LineDetectorB200(bad)
+    flat = np.full((80, 160, 3), 60, np.uint8)
+    det.setImage(flat)
+    assert det.detectLines('white').lines == []
+
+
+def test_project_filter_given_oracle_endpoints(mods):
+    """K12 on identical inputs: ground points <= 1e-4 m, keep mask exact (incl. clamp / v>H-1 -> 0 quirk)."""
+    L, cm, rg, synth, cfg = mods
+    rng = np.random.default_rng(0)
+    pix = rng.uniform(-0.1, 1.1, (5000, 4)).astype(np.float32)
+    col = rng.integers(0, 3, 5000).astype(np.uint8)
+    fe = L.FrontEnd(max_batch=1)
+    g, keep = fe.project_filter(pix, col)
+    gp = rg.GroundProjection()
+    ref = gp.project_segments(pix)
+    ok = np.isfinite(ref).all(axis=1)
+    rel = np.abs(g[ok] - ref[ok]) / np.maximum(1.0, np.abs(ref[ok]))
+    assert rel.max() <= GROUND_TOL_M
+    # keep mask against the oracle C model given the same ground points
+    _, g2, k2 = cm.project_filter(pix * np.array([160, 120, 160, 120], np.float32) - np.array([0, 40, 0, 40], np.float32),
+                                  col, (120, 160), 40, rg.DEFAULT_CAMERA, rg.DEFAULT_HOMOGRAPHY)
+    refkeep = rg.sanity_keep(g, col)
+    assert np.array_equal(keep, refkeep)
+    fe.close()
+
+
+def test_knn_hamming_exact_with_ties(mods):
+    """K13: indices bit-exact vs the oracle and cv2.BFMatcher; duplicated rows -> smallest index wins."""
+    L, cm, rg, synth, cfg = mods
+    q, m, src = synth.descriptor_sets(700, 30000, seed=3)
+    fe = L.FrontEnd(max_batch=1)
+    for k in (1, 2, 5):
+        idx, dist = fe.knn(q, m, k=k)
+        oi, od = cm.knn_hamming(q, m, k)
+        assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+    idx, dist = fe.knn(q, m, k=2)
+    bi, bd = rg.knn_hamming_bf(q, m, 2)
+    assert np.array_equal(idx, bi) and np.array_equal(dist, bd)
+    assert (idx[:64, 0] == np.arange(64)).all()          # duplicated block: lower index wins
+    # Mihasher radius D=128: farther neighbours are not reported
+    far = np.bitwise_not(m[:5])
+    idx, dist = fe.knn(far, m[:5], k=1, max_dist=128)
+    assert (idx == -1).all() and (dist == -1).all()
+    # fewer map rows than k
+    idx, dist = fe.knn(q[:3], m[:2], k=4)
+    assert (idx[:, 2:] == -1).all()
+    fe.close()
+
+
+def test_full_size_knn_properties(mods):
+    """C4 size (2 000 x 100 000): self-match at distance 0, symmetric distances, nearest = planted row."""
+    L, cm, rg, synth, cfg = mods
+    q, m, src = synth.descriptor_sets(2000, 100000, seed=0)
+    fe = L.FrontEnd(max_batch=1)
+    idx, dist = fe.knn(q, m, k=2)
+    assert np.array_equal(idx[:, 0], np.where(src >= 100000 - 64, src - (100000 - 64), src))
+    d_true = np.unpackbits(q ^ m[idx[:, 0]], axis=1).sum(axis=1)
+    assert np.array_equal(d_true, dist[:, 0])
+    assert (dist[:, 0] <= dist[:, 1]).all()
+    i2, d2 = fe.knn(m[:500], m, k=1)
+    assert (d2[:, 0] == 0).all() and (i2[:, 0] <= np.arange(500)).all()
+    fe.close()
+
+
+def test_match_stage_frame_to_frame(mods):
+    """C2-style association: descriptors of frame t matched against the map built from frame t-1."""
+    L, cm, rg, synth, cfg = mods
+    frames = synth.sequence(3, base_seed=11)
+    fe, cam, Hg = _front_end(L, rg, (480, 640), 0, 480, 640, 1)
+    b0 = fe.process(frames[0:1], stages=L.STAGE_DETECT | L.STAGE_GROUND | L.STAGE_DESCRIBE)
+    d0 = b0.desc.copy()
+    fe.map_clear(); fe.map_add(d0)
+    assert fe.map_size() == len(d0)
+    b1 = fe.process(frames[1:2], stages=L.STAGE_DETECT | L.STAGE_GROUND | L.STAGE_DESCRIBE | L.STAGE_MATCH, k=2)
+    oi, od = cm.knn_hamming(b1.desc, d0, 2)
+    assert np.array_equal(b1.match_idx, oi) and np.array_equal(b1.match_dist, od)
+    fe.close()
+
+
+def test_capacity_errors_are_loud(mods):
+    L, cm, rg, synth, cfg = mods
+    fe = L.FrontEnd(dict(L.DEFAULT_DETECTOR_CONFIGURATION), img_size=(480, 640), top_cutoff=0, max_batch=1,
+                    max_segments_per_color=4)
+    with pytest.raises(L.LsfError) as e:
+        fe.process(synth.frame(0))
+    assert e.value.code == -3
+    fe.close()
+    fe = L.FrontEnd(dict(L.DEFAULT_DETECTOR_CONFIGURATION), img_size=(480, 640), top_cutoff=0, max_batch=1)
+    with pytest.raises(L.LsfError):
+        fe.process(np.zeros((2, 480, 640, 3), np.uint8))       # n > max_batch
+    fe.close()
+    with pytest.raises(ValueError):
+        L.FrontEnd(dict(L.DEFAULT_DETECTOR_CONFIGURATION, dilation_kernel_size=5))
+
+
+def test_device_resident_input_and_determinism(mods):
+    """Frames already in HBM (torch CUDA tensor) give the same result as host frames; two runs agree."""
+    import torch
+    L, cm, rg, synth, cfg = mods
+    frames = np.stack([synth.frame(s) for s in range(300, 308)])
+    fe, cam, Hg = _front_end(L, rg, (480, 640), 0, 480, 640, 8)
+    st = L.STAGE_DETECT | L.STAGE_GROUND | L.STAGE_DESCRIBE
+    b = fe.process(frames, stages=st)
+    ref = (b.counts.copy(), b.lines_px.copy(), b.desc.copy(), b.keep.copy())
+    t = torch.from_numpy(frames).cuda()
+    for _ in range(2):
+        b = fe.process(t, stages=st)
+        assert np.array_equal(b.counts, ref[0]) and np.array_equal(b.lines_px, ref[1])
+        assert np.array_equal(b.desc, ref[2]) and np.array_equal(b.keep, ref[3])
+    fe.close()
