@@ -34,6 +34,7 @@ struct Dims {
     int segcap;            // segment capacity per colour image
     int identity_geom;     // 1: no resize (dh==src_h, dw==src_w)
     int identity_color;    // 1: AntiInstagram scale==1, shift==0
+    int debug;             // LSF_TRACE_LSD: device printf of every LSD candidate
 };
 
 // one entry per 32 scaled pixels: defined-angle bits + number of defined pixels before this word

@@ -10,7 +10,9 @@
 // pixel), because the result depends on it; the warp evaluates the nine neighbours of a point in
 // parallel and resolves acceptances in order.  Rectangle sums, the NFA pixel scan and the seed sort are
 // warp-parallel (ballot / shuffle reductions, stable counting sort with match_any).
+#include <cstdio>
 #include "common.cuh"
+#include "sincos_cr.cuh"
 
 namespace lsf {
 
@@ -235,7 +237,9 @@ __device__ void region2rect(const Img &im, Seq3 &sm, int nreg, double reg_angle,
                                            : (double)fast_atan2_deg((float)Ixy, (float)(lambda - Iyy));
     theta *= kDEG2RAD;
     if (fabs(angle_diff_signed(theta, reg_angle)) > prec) theta += kPI;
-    double dx = cos(theta), dy = sin(theta);
+    // the last bit of cos/sin decides pixel membership at rectangle corners: use the correctly rounded pair
+    double dx, dy;
+    if (!sincos_cr(theta, &dy, &dx)) { dx = cos(theta); dy = sin(theta); }
     // extents: min / max are order independent
     double lmin = 0, lmax = 0, wmn = 0, wmx = 0;
     for (int i = lane; i < nreg; i += 32) {
@@ -372,7 +376,7 @@ __device__ __forceinline__ double slope_d(double ax, double ay, double bx, doubl
     return (ceil(by) != ceil(ay)) ? (bx - ax) / (by - ay) : 0.0;
 }
 
-__device__ double rect_nfa(const Img &im, const Rect &r)
+__device__ double rect_nfa(const Img &im, const Rect &r, bool verbose = false)
 {
     const int lane = threadIdx.x & 31;
     double hw = r.width / 2.0, dyhw = r.dy * hw, dxhw = r.dx * hw;
@@ -402,6 +406,7 @@ __device__ double rect_nfa(const Img &im, const Rect &r)
             xa = max(to_int_x86(ceil(ll)), 0);
             int xb = min(to_int_x86(rl), im.W - 1);
             cnt = xb >= xa ? xb - xa + 1 : 0;
+            if (verbose) printf("   row %d ll=%.6f rl=%.6f xa=%d xb=%d\n", y, ll, rl, xa, xb);
         }
         // inclusive scan of the span lengths
         int incl = cnt;
@@ -429,6 +434,7 @@ __device__ double rect_nfa(const Img &im, const Rect &r)
         }
     }
     alg = __reduce_add_sync(FULL, alg);
+    if (verbose && lane == 0) printf("   tot=%d alg=%d ys=%d ye=%d\n", tot, alg, ys, ye);
     return nfa_d(tot, alg, r.p, im.logNT);
 }
 
@@ -564,8 +570,16 @@ __global__ void __launch_bounds__(32) k_lsd_core(Dims d, const LsdWord *__restri
             if (nreg < min_reg) continue;
             Rect rec;
             region2rect(im, sm, nreg, reg_angle, prec, p, rec);
-            if (!refine(im, sm, nreg, reg_angle, prec, p, rec)) continue;
+            const int nreg0 = nreg;
+            if (!refine(im, sm, nreg, reg_angle, prec, p, rec)) {
+                if (d.debug && lane == 0) printf("img %d cand seed=(%d,%d) refine-rejected nreg=%d nreg0=%d\n", img, im.xy[seed] & 0xffff, im.xy[seed] >> 16, nreg, nreg0);
+                continue;
+            }
             double log_nfa = rect_improve(im, rec);
+            if (d.debug && lane == 0)
+                printf("img %d cand seed=(%d,%d) nreg=%d nreg0=%d nfa=%.17g p=%g w=%g (%.3f,%.3f)-(%.3f,%.3f)\n", img, im.xy[seed] & 0xffff,
+                       im.xy[seed] >> 16, nreg, nreg0, log_nfa, rec.p, rec.width, rec.x1, rec.y1, rec.x2, rec.y2);
+            if (d.debug > 1) rect_nfa(im, rec, true);
             if (!(log_nfa > 0.0)) continue;
             if (nout < d.segcap && lane == 0) {
                 LsdSeg s;
@@ -584,6 +598,11 @@ __global__ void __launch_bounds__(32) k_lsd_core(Dims d, const LsdWord *__restri
 
 void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st)
 {
+    static bool tab_ready = false;
+    if (!tab_ready) {
+        cudaMemcpyToSymbol(c_sincos_tab, scr::kSinCosTab, sizeof(scr::kSinCosTab));
+        tab_ready = true;
+    }
     k_lsd_core<<<d.n * 3, 32, 0, st>>>(d, b.lsdw, b.pix, b.pixxy, b.used, b.order, b.reg, b.pixcount, b.g2max, b.rawseg,
                                        b.segcount, b.flags);
     ++g_launches;

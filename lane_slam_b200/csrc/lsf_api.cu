@@ -148,7 +148,9 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     ctx->sw = (int)lrint(ctx->w * 0.8); ctx->sh = (int)lrint(ctx->h * 0.8);
     ctx->swp = (ctx->sw + 31) / 32;
     const size_t Np = (size_t)ctx->sh * ctx->sw;
-    ctx->pixcap = cfg->max_pixels_per_color > 0 ? cfg->max_pixels_per_color : (int)std::max<size_t>(4096, Np / 4);
+    // default: every scaled pixel may be a support pixel for small batches; a quarter of them for large ones
+    ctx->pixcap = cfg->max_pixels_per_color > 0 ? cfg->max_pixels_per_color
+                                                : (int)(ctx->max_batch <= 128 ? Np : std::max<size_t>(4096, Np / 4));
     if ((size_t)ctx->pixcap > Np) ctx->pixcap = (int)Np;
     ctx->segcap = cfg->max_segments_per_color > 0 ? cfg->max_segments_per_color
                                                   : (int)std::max<size_t>(512, (size_t)ctx->h * ctx->w / 256);
@@ -341,6 +343,7 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
     d.h = ctx->h; d.w = ctx->w; d.wp = ctx->wp; d.sh = ctx->sh; d.sw = ctx->sw; d.swp = ctx->swp;
     d.pixcap = ctx->pixcap; d.segcap = ctx->segcap;
     d.identity_geom = (d.dh == src_h && d.dw == src_w);
+    d.debug = getenv("LSF_TRACE_LSD") ? atoi(getenv("LSF_TRACE_LSD")) : 0;
     for (int i = 0; i < 3; ++i) { ctx->cp.ai_scale[i] = ctx->cfg.ai_scale[i]; ctx->cp.ai_shift[i] = ctx->cfg.ai_shift[i]; }
     d.identity_color = 1;
     for (int i = 0; i < 3; ++i) if (ctx->cp.ai_scale[i] != 1.f || ctx->cp.ai_shift[i] != 0.f) d.identity_color = 0;

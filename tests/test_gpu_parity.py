@@ -210,7 +210,7 @@ def test_knn_hamming_exact_with_ties(mods):
     assert (idx[:64, 0] == np.arange(64)).all()          # duplicated block: lower index wins
     # Mihasher radius D=128: farther neighbours are not reported
     far = np.bitwise_not(m[:5])
-    idx, dist = fe.knn(far, m[:5], k=1, max_dist=128)
+    idx, dist = fe.knn(far, m[:5], k=1, max_dist=64)
     assert (idx == -1).all() and (dist == -1).all()
     # fewer map rows than k
     idx, dist = fe.knn(q[:3], m[:2], k=4)
