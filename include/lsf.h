@@ -103,7 +103,9 @@ enum {
     LSF_STAGE_DETECT = 1,   /* line_detector_node: resize/crop/colour-correct, HSV masks, Canny, 3x LSD, normals */
     LSF_STAGE_GROUND = 2,   /* ground_projection_node + line_sanity_node */
     LSF_STAGE_DESCRIBE = 4, /* LSDDetectorC KeyLine fill + BinaryDescriptor::compute */
-    LSF_STAGE_MATCH = 8     /* BinaryDescriptorMatcher::knnMatch against the ctx map */
+    LSF_STAGE_MATCH = 8,    /* BinaryDescriptorMatcher::knnMatch against the ctx map */
+    LSF_STAGE_MATCH_PREV = 16 /* knnMatch(frame t, frame t-1): frame-to-frame association; trainIdx is local to frame t-1;
+                                 frame 0 of a batch matches the last frame of the previous batch (lsf_reset_sequence clears it) */
 };
 
 /* debug / parity taps (dense per-frame maps, one byte per pixel, 0/255 or label values) */
@@ -167,6 +169,9 @@ LSF_API int lsf_knn_hamming(lsf_ctx *ctx, const uint8_t *query, int nq, const ui
 LSF_API int lsf_map_clear(lsf_ctx *ctx);
 LSF_API int lsf_map_add(lsf_ctx *ctx, const uint8_t *desc, int n, int mem_kind);
 LSF_API int lsf_map_size(lsf_ctx *ctx);
+
+/* Forget the previous batch's last frame (start of a new sequence for LSF_STAGE_MATCH_PREV). */
+LSF_API int lsf_reset_sequence(lsf_ctx *ctx);
 
 /* Parity taps: copy a dense stage map of frame `frame` of the last batch to host memory `dst`. */
 LSF_API int lsf_get_tap(lsf_ctx *ctx, int tap, int frame, void *dst, size_t dst_bytes);

@@ -6,7 +6,7 @@ descriptors and Hamming association): the plugin class ``LineDetectorB200`` mirr
 ``liblsf.so`` (hand-written CUDA behind the C ABI of include/lsf.h); importing this package never
 touches ``oracle/`` and there is no CPU fallback.
 """
-from ._lib import (LsfError, STAGE_DESCRIBE, STAGE_DETECT, STAGE_GROUND, STAGE_MATCH, MEM_DEVICE, MEM_HOST,
+from ._lib import (LsfError, STAGE_DESCRIBE, STAGE_DETECT, STAGE_GROUND, STAGE_MATCH, STAGE_MATCH_PREV, MEM_DEVICE, MEM_HOST,
                    LIB_PATH, exported_symbols)
 from .frontend import (FrontEnd, SegmentBatch, DEFAULT_DETECTOR_CONFIGURATION, DETECTOR_PARAM_NAMES, COLORS,
                        WHITE, YELLOW, RED, scaled_calibration, check_detector_configuration)

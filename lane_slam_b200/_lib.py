@@ -7,7 +7,7 @@ LIB_PATH = os.path.join(_HERE, "liblsf.so")
 
 LSF_OK, LSF_E_CONFIG, LSF_E_ARG, LSF_E_CAPACITY, LSF_E_CUDA, LSF_E_NCCL, LSF_E_INTERNAL = 0, -1, -2, -3, -4, -5, -6
 MEM_HOST, MEM_PINNED, MEM_DEVICE = 0, 1, 2
-STAGE_DETECT, STAGE_GROUND, STAGE_DESCRIBE, STAGE_MATCH = 1, 2, 4, 8
+STAGE_DETECT, STAGE_GROUND, STAGE_DESCRIBE, STAGE_MATCH, STAGE_MATCH_PREV = 1, 2, 4, 8, 16
 TAP = dict(image=0, labels=1, edges=2, bw_white=3, bw_yellow=4, bw_red=5, ec_white=6, ec_yellow=7, ec_red=8,
            gray=9, dx=10, dy=11)
 
@@ -41,7 +41,7 @@ class LsfSegments(C.Structure):
 _EXPORTS = [
     "lsf_default_config", "lsf_create", "lsf_destroy", "lsf_last_error", "lsf_set_color_transform",
     "lsf_front_end_batch", "lsf_detect_batch", "lsf_describe_batch", "lsf_project_filter_batch",
-    "lsf_knn_hamming", "lsf_map_clear", "lsf_map_add", "lsf_map_size", "lsf_get_tap", "lsf_image_dims",
+    "lsf_knn_hamming", "lsf_map_clear", "lsf_map_add", "lsf_map_size", "lsf_reset_sequence", "lsf_get_tap", "lsf_image_dims",
     "lsf_last_timings", "lsf_launch_count", "lsf_stream", "lsf_version",
 ]
 
@@ -79,6 +79,7 @@ def load():
     lib.lsf_map_clear.argtypes = [vp]
     lib.lsf_map_add.argtypes = [vp, vp, i32, i32]
     lib.lsf_map_size.argtypes = [vp]
+    lib.lsf_reset_sequence.argtypes = [vp]
     lib.lsf_get_tap.argtypes = [vp, i32, i32, vp, sz]
     lib.lsf_image_dims.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.lsf_last_timings.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), i32]

@@ -105,6 +105,8 @@ void launch_project_filter(const CamParams &cam, const float *pixn, const u8 *co
 void launch_knn(const u8 *q, int nq_cap, const int *nq_dev, const u8 *m, int nm, int k, int max_dist, int *idx, int *dist,
                 void *scratch, size_t scratch_bytes, cudaStream_t st);
 size_t knn_scratch_bytes(int nq, int nm, int k);
+void launch_knn_prev(const u8 *desc, const int *frame_off, int n, int k, int max_dist, const u8 *carry, int carry_n, int *idx,
+                     int *dist, cudaStream_t st);
 void launch_unpack_plane(const u32 *plane, int h, int w, int wp, u8 *dst, cudaStream_t st);
 void launch_labels_tap(const u32 *planesA_frame, int h, int w, int wp, u8 *dst, cudaStream_t st);
 void launch_image_tap(const Dims &d, const ColorParams &cp, const u8 *src_frame, u8 *dst, cudaStream_t st);

@@ -92,6 +92,61 @@ __global__ void k_knn_merge(int nq_cap, const int *__restrict__ nq_dev, int nspl
     }
 }
 
+// ---- frame-to-frame association: queries = segments of frame f, train = segments of frame f-1 ----------
+// (with one GPU and an epoch of one frame the map snapshot is the previous frame.)  One CTA
+// per frame; frame 0 matches the carry (last frame of the previous batch).  trainIdx is the index inside
+// the previous frame's segment list.
+template <int K>
+__global__ void __launch_bounds__(128) k_knn_prev(const uint4 *__restrict__ desc, const int *__restrict__ frame_off, int k, int max_dist,
+                                                 const uint4 *__restrict__ carry, int carry_n, int *__restrict__ idx,
+                                                 int *__restrict__ dist)
+{
+    __shared__ uint4 tile[128 * 2];
+    const int f = blockIdx.x;
+    const int q0 = frame_off[f], q1 = frame_off[f + 1];
+    const uint4 *tp; int nt;
+    if (f > 0) { int t0 = frame_off[f - 1]; tp = desc + 2 * (size_t)t0; nt = q0 - t0; }
+    else { tp = carry; nt = carry_n; }
+    for (int qb = q0; qb < q1; qb += 128) {
+        const int qi = qb + threadIdx.x;
+        uint4 qa = make_uint4(0, 0, 0, 0), qbv = qa;
+        if (qi < q1) { qa = desc[2 * (size_t)qi]; qbv = desc[2 * (size_t)qi + 1]; }
+        int bd[K], bi[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) { bd[j] = 0x7fffffff; bi[j] = -1; }
+        for (int t0 = 0; t0 < nt; t0 += 128) {
+            const int m = min(128, nt - t0);
+            __syncthreads();
+            for (int i = threadIdx.x; i < m * 2; i += 128) tile[i] = tp[2 * (size_t)t0 + i];
+            __syncthreads();
+            for (int j = 0; j < m; ++j) {
+                uint4 a = tile[2 * j], b = tile[2 * j + 1];
+                int dd = __popc(qa.x ^ a.x) + __popc(qa.y ^ a.y) + __popc(qa.z ^ a.z) + __popc(qa.w ^ a.w) +
+                         __popc(qbv.x ^ b.x) + __popc(qbv.y ^ b.y) + __popc(qbv.z ^ b.z) + __popc(qbv.w ^ b.w);
+                if (dd < bd[K - 1] && dd <= max_dist) knn_insert<K>(bd, bi, dd, t0 + j);
+            }
+        }
+        if (qi < q1) {
+            for (int j = 0; j < k; ++j) {
+                bool ok = j < K && bi[j < K ? j : 0] >= 0;
+                idx[(size_t)qi * k + j] = ok ? bi[j] : -1;
+                dist[(size_t)qi * k + j] = ok ? bd[j] : -1;
+            }
+        }
+    }
+}
+
+void launch_knn_prev(const u8 *desc, const int *frame_off, int n, int k, int max_dist, const u8 *carry, int carry_n, int *idx,
+                     int *dist, cudaStream_t st)
+{
+    const uint4 *d4 = (const uint4 *)desc, *c4 = (const uint4 *)carry;
+    if (k <= 1) k_knn_prev<1><<<n, 128, 0, st>>>(d4, frame_off, k, max_dist, c4, carry_n, idx, dist);
+    else if (k <= 2) k_knn_prev<2><<<n, 128, 0, st>>>(d4, frame_off, k, max_dist, c4, carry_n, idx, dist);
+    else if (k <= 4) k_knn_prev<4><<<n, 128, 0, st>>>(d4, frame_off, k, max_dist, c4, carry_n, idx, dist);
+    else k_knn_prev<8><<<n, 128, 0, st>>>(d4, frame_off, k, max_dist, c4, carry_n, idx, dist);
+    ++g_launches;
+}
+
 static int knn_K(int k) { return k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : 8; }
 
 static int knn_nsplit(int nq, int nm)

@@ -34,6 +34,8 @@ struct lsf_ctx {
     int map_n, map_cap;
     void *knn_scratch;
     size_t knn_scratch_cap;
+    u8 *carry;            // descriptors of the last frame of the previous batch
+    int carry_n, carry_cap;
     // pinned host staging
     int *h_small;         // [n*3 + n+1 + 4]
     u8 *tap_tmp;
@@ -209,7 +211,7 @@ extern "C" void lsf_destroy(lsf_ctx *ctx)
     void *ptrs[] = {b.src, b.planesA, b.planesB, b.gray, b.dx, b.lsdw, b.pix, b.pixxy, b.used, b.order, b.reg, b.pixcount,
                     b.g2max, b.rawseg, b.segcount, b.frame_off, b.flags, b.o_color, b.o_lines, b.o_normals, b.o_centers,
                     b.o_pixn, b.o_nf32, b.o_ground, b.o_keep, b.o_desc, b.o_frame, b.o_midx, b.o_mdist, ctx->map,
-                    ctx->knn_scratch, ctx->tap_tmp, ctx->seg_in};
+                    ctx->knn_scratch, ctx->tap_tmp, ctx->seg_in, ctx->carry};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
     for (auto &e : ctx->events) cudaEventDestroy(e.ev);
@@ -332,9 +334,12 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
         return fail(ctx, LSF_E_CAPACITY, "lsf_front_end_batch: frame larger than max_src_h x max_src_w");
     if (pitch < (size_t)src_w * 3) return fail(ctx, LSF_E_ARG, "lsf_front_end_batch: pitch smaller than a row");
     if (!(stages & LSF_STAGE_DETECT)) return fail(ctx, LSF_E_ARG, "lsf_front_end_batch: stages must include LSF_STAGE_DETECT");
-    if ((stages & LSF_STAGE_MATCH) && !(stages & LSF_STAGE_DESCRIBE))
-        return fail(ctx, LSF_E_ARG, "lsf_front_end_batch: LSF_STAGE_MATCH needs LSF_STAGE_DESCRIBE");
-    if ((stages & LSF_STAGE_MATCH) && (k < 1 || k > 8)) return fail(ctx, LSF_E_ARG, "lsf_front_end_batch: k must be 1..8");
+    const int any_match = stages & (LSF_STAGE_MATCH | LSF_STAGE_MATCH_PREV);
+    if (any_match && !(stages & LSF_STAGE_DESCRIBE))
+        return fail(ctx, LSF_E_ARG, "lsf_front_end_batch: matching needs LSF_STAGE_DESCRIBE");
+    if ((stages & LSF_STAGE_MATCH) && (stages & LSF_STAGE_MATCH_PREV))
+        return fail(ctx, LSF_E_ARG, "lsf_front_end_batch: choose one of LSF_STAGE_MATCH / LSF_STAGE_MATCH_PREV");
+    if (any_match && (k < 1 || k > 8)) return fail(ctx, LSF_E_ARG, "lsf_front_end_batch: k must be 1..8");
     CK(cudaSetDevice(ctx->device));
     Buffers &b = ctx->b;
     Dims d;
@@ -404,6 +409,19 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
         launch_knn(b.o_desc, S, nullptr, ctx->map, ctx->map_n, k, 256, b.o_midx, b.o_mdist, ctx->knn_scratch, ctx->knn_scratch_cap, ctx->st);
         mark(ctx, "knn");
     }
+    if ((stages & LSF_STAGE_MATCH_PREV) && S > 0) {
+        if (!b.o_midx) { CK(dalloc(&b.o_midx, (size_t)b.outcap * 8)); CK(dalloc(&b.o_mdist, (size_t)b.outcap * 8)); }
+        if (!ctx->carry) { ctx->carry_cap = 3 * ctx->segcap; CK(cudaMalloc((void **)&ctx->carry, (size_t)ctx->carry_cap * 32)); }
+        launch_knn_prev(b.o_desc, b.frame_off, n, k, 256, ctx->carry, ctx->carry_n, b.o_midx, b.o_mdist, ctx->st);
+        mark(ctx, "knn_prev");
+    }
+    if (stages & LSF_STAGE_MATCH_PREV) {
+        // keep the last frame's descriptors for the next batch
+        int l0 = hs[n * 3 + n - 1], l1 = hs[n * 3 + n];
+        if (!ctx->carry) { ctx->carry_cap = 3 * ctx->segcap; CK(cudaMalloc((void **)&ctx->carry, (size_t)ctx->carry_cap * 32)); }
+        ctx->carry_n = l1 - l0;
+        if (ctx->carry_n > 0) CK(cudaMemcpyAsync(ctx->carry, b.o_desc + (size_t)l0 * 32, (size_t)ctx->carry_n * 32, cudaMemcpyDeviceToDevice, ctx->st));
+    }
     const cudaMemcpyKind kind = out_kind(out->mem);
     if (out->counts) {
         if (out->mem == LSF_MEM_DEVICE) CK(cudaMemcpyAsync(out->counts, b.segcount, (size_t)n * 3 * sizeof(int), kind, ctx->st));
@@ -424,7 +442,7 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
         COPY(out->normal_f32, b.o_nf32, s * 8);
         if (stages & LSF_STAGE_GROUND) { COPY(out->ground, b.o_ground, s * 32); COPY(out->keep, b.o_keep, s); }
         if (stages & LSF_STAGE_DESCRIBE) COPY(out->desc, b.o_desc, s * 32);
-        if (stages & LSF_STAGE_MATCH) { COPY(out->match_idx, b.o_midx, s * k * 4); COPY(out->match_dist, b.o_mdist, s * k * 4); }
+        if (any_match) { COPY(out->match_idx, b.o_midx, s * k * 4); COPY(out->match_dist, b.o_mdist, s * k * 4); }
 #undef COPY
     }
     mark(ctx, "d2h");
@@ -557,6 +575,13 @@ extern "C" int lsf_map_clear(lsf_ctx *ctx)
 }
 
 extern "C" int lsf_map_size(lsf_ctx *ctx) { return ctx ? ctx->map_n : LSF_E_ARG; }
+
+extern "C" int lsf_reset_sequence(lsf_ctx *ctx)
+{
+    if (!ctx) return LSF_E_ARG;
+    ctx->carry_n = 0;
+    return LSF_OK;
+}
 
 extern "C" int lsf_map_add(lsf_ctx *ctx, const uint8_t *desc, int n, int mem_kind)
 {

@@ -13,7 +13,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (LsfConfig, LsfError, LsfSegments, MEM_DEVICE, MEM_HOST, STAGE_DESCRIBE, STAGE_DETECT,
-                   STAGE_GROUND, STAGE_MATCH, TAP)
+                   STAGE_GROUND, STAGE_MATCH, STAGE_MATCH_PREV, TAP)
 
 WHITE, YELLOW, RED = 0, 1, 2          # src/duckietown_msgs/msg/Segment.msg:1-3
 COLORS = ("white", "yellow", "red")
@@ -194,10 +194,7 @@ class FrontEnd:
         for name in ("counts", "frame_offset", "color", "lines_px", "normals", "centers", "pixels_normalized",
                      "normal_f32", "ground", "keep", "desc", "match_idx", "match_dist"):
             setattr(seg, name, a[name].ctypes.data)
-        kk = int(k) if (stages & STAGE_MATCH) else 0
-        if kk:
-            # match arrays are [S][k] packed
-            pass
+        kk = int(k) if (stages & (STAGE_MATCH | STAGE_MATCH_PREV)) else 0
         rc = self._lib.lsf_front_end_batch(self._ctx, ptr, n, H, W, W * 3, kind, int(stages), kk, C.byref(seg))
         self._check(rc)
         del dev_ptr
@@ -250,6 +247,10 @@ class FrontEnd:
         """Device-resident variant (raw device pointers)."""
         self._check(self._lib.lsf_knn_hamming(self._ctx, q_ptr, nq, m_ptr, nm, int(k), int(max_dist), MEM_DEVICE,
                                               idx_ptr, dist_ptr))
+
+    def reset_sequence(self):
+        """Start a new sequence for STAGE_MATCH_PREV (forget the previous batch's last frame)."""
+        self._check(self._lib.lsf_reset_sequence(self._ctx))
 
     def map_clear(self):
         self._check(self._lib.lsf_map_clear(self._ctx))
