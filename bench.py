@@ -131,7 +131,7 @@ def cpu_baseline(sample_frames, cores):
     import multiprocessing as mp
     per = max(1, sample_frames // cores)
     jobs = [(1000 + i * per, per) for i in range(cores)]
-    ctx = mp.get_context("fork")
+    ctx = mp.get_context("spawn")     # never fork a process that may hold CUDA / OpenMP state
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
         res = pool.map(_cpu_worker, jobs)
@@ -145,7 +145,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, len(os.sched_getaffinity(0)))
     sample = max(cores * 4, 64)
     vals = []
     for i in range(args.warmup + args.steps):
@@ -184,7 +184,14 @@ def run_gpu(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = args.frames
+    t_start = time.perf_counter()
+
+    def log(msg):
+        if rank == 0 and args.verbose:
+            print("[bench %.1fs] %s" % (time.perf_counter() - t_start, msg), file=sys.stderr, flush=True)
+
     frames_np = make_frames(n, base_seed=rank * n)            # this rank's shard of the log
+    log("frames generated")
     pinned = torch.from_numpy(frames_np).pin_memory()
     dev = pinned.cuda(non_blocking=False)
     fe = L.FrontEnd(dict(L.DEFAULT_DETECTOR_CONFIGURATION), img_size=(H, W), top_cutoff=0, src_size=(H, W), max_batch=n,
@@ -227,10 +234,13 @@ def run_gpu(args):
         dt = e0.elapsed_time(e1) * 1e-3
         return dt, stage_ms, d2h, b
 
+    log("context ready")
     # warm-up (>= 3)
-    for _ in range(max(3, args.warmup)):
-        step(dev)
+    for i in range(max(3, args.warmup)):
+        b = step(dev)
+        log("warmup %d: S=%d %s" % (i, b.n_segments, ["%s=%.2f" % x for x in fe.timings()]))
     step(pinned.numpy())
+    log("warmup host path done")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -282,12 +292,15 @@ def run_gpu(args):
         "roofline": roofline, "kernels": kernels, "clocks": clocks,
     }
     if world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        sample = max(cores * 4, 64)
-        fps, total, wall = cpu_baseline(sample, cores)
-        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                                "sample": "%d frames of the same workload, %d single-threaded cv2 workers (restated reference "
-                                          "glue + cv2 4.13, C LBD, cv2.BFMatcher), %.1f s wall" % (total, cores, wall)}
+        # the CPU leg runs in a fresh interpreter (no CUDA state), bounded in time
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                                 capture_output=True, text=True, timeout=600)
+            ref = json.loads(out.stdout.strip().splitlines()[-1])
+            line["cpu_baseline"] = ref["cpu_baseline"]
+        except Exception as e:  # the GPU numbers stand on their own
+            line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "failed: %r" % (e,)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -301,6 +314,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=N_FRAMES, help="frames per step per GPU (default: the 1000-frame workload)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--verbose", action="store_true", help="progress on stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
