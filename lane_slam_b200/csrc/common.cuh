@@ -63,6 +63,9 @@ struct CamParams {
 // raw LSD output per accepted segment (before normals / ordering)
 struct LsdSeg { float x1, y1, x2, y2; };
 
+// rectangle candidate handed from the growing kernel to the NFA validation kernel
+struct LsdCand { double x1, y1, x2, y2, width, theta, dx, dy; };
+
 // ---- device buffers of a context ------------------------------------------------------------------
 struct Buffers {
     u8 *src;            // staged input frames (when the caller passes host memory)
@@ -78,10 +81,15 @@ struct Buffers {
     u32 *reg;           // [n*3][2*pixcap] region point list + scratch
     int *pixcount;      // [n*3]
     u32 *g2max;         // [n*3]
+    LsdCand *cand;      // [n*3][segcap]  candidates after refine, in seed order
+    int *candcount;     // [n*3]
+    uint2 *candlist;    // [n*3*segcap]   flat (image, candidate) work list for the validation kernel
+    LsdSeg *candseg;    // [n*3][segcap]  validated endpoints
+    u8 *candok;         // [n*3][segcap]  1 iff NFA accepted
     LsdSeg *rawseg;     // [n*3][segcap]
     int *segcount;      // [n*3]
     int *frame_off;     // [n+1]
-    int *flags;         // [4] overflow flags: 0 pix overflow, 1 seg overflow, 2 out capacity
+    int *flags;         // [4] 0 pix overflow, 1 seg/candidate overflow, 2 out capacity, 3 candidate counter
     // compacted per-segment outputs (capacity outcap)
     int outcap;
     u8 *o_color; float *o_lines; double *o_normals; float *o_centers; float *o_pixn; float *o_nf32;

@@ -11,6 +11,7 @@
 // parallel and resolves acceptances in order.  Rectangle sums, the NFA pixel scan and the seed sort are
 // warp-parallel (ballot / shuffle reductions, stable counting sort with match_any).
 #include <cstdio>
+#include <vector>
 #include "common.cuh"
 #include "sincos_cr.cuh"
 
@@ -80,7 +81,7 @@ __device__ __forceinline__ double angle_diff_signed(double a, double b)
 }
 
 // ---- NFA (all lanes compute the same value) -------------------------------------------------------
-__device__ double log_gamma_d(double x)
+__host__ __device__ inline double log_gamma_d(double x)
 {
     if (x > 15.0)
         return 0.918938533204673 + (x - 0.5) * log(x) - x + 0.5 * x * log(x * sinh(1 / x) + 1 / (810.0 * pow(x, 6.0)));
@@ -102,12 +103,22 @@ __device__ bool double_equal_d(double a, double b)
     return (diff / m) <= 100.0 * 2.220446049250313e-16;
 }
 
+// log_gamma of the integers 0..LGTAB-1, evaluated on the host with the same formulas (and the host libm
+// the reference itself runs on); rect_nfa only ever asks for integer arguments.
+constexpr int LGTAB = 16384;
+__device__ const double *g_lgtab;
+
+__device__ __forceinline__ double lg_int(int v)
+{
+    return v < LGTAB ? g_lgtab[v] : log_gamma_d((double)v);
+}
+
 __device__ double nfa_d(int n, int k, double p, double logNT)
 {
     if (n == 0 || k == 0) return -logNT;
     if (n == k) return -logNT - (double)n * log10(p);
     double p_term = p / (1 - p);
-    double log1term = log_gamma_d((double)n + 1) - log_gamma_d((double)k + 1) - log_gamma_d((double)(n - k) + 1) +
+    double log1term = lg_int(n + 1) - lg_int(k + 1) - lg_int(n - k + 1) +
                       (double)k * log(p) + (double)(n - k) * log(1.0 - p);
     double term = exp(log1term);
     if (double_equal_d(term, 0)) {
@@ -483,17 +494,13 @@ __device__ double rect_improve(const Img &im, Rect &rec)
     return log_nfa;
 }
 
-// ---- the kernel: one warp per (frame, colour) image -------------------------------------------------------
-__global__ void __launch_bounds__(32) k_lsd_core(Dims d, const LsdWord *__restrict__ lsdw, const LsdPix *__restrict__ pix,
-                                                const u32 *__restrict__ pixxy, u8 *__restrict__ used, u32 *__restrict__ order,
-                                                u32 *__restrict__ reg, const int *__restrict__ pixcount,
-                                                const u32 *__restrict__ g2max, LsdSeg *__restrict__ rawseg,
-                                                int *__restrict__ segcount, int *__restrict__ flags)
+// ---- kernel 1: seeds, region growing, rectangle fit, density refinement -> candidate rectangles ----------
+// One warp per (frame, colour) image; strictly sequential in the reference's seed order because growing and
+// refining change which pixels later seeds may use.  NFA validation does not touch that state, so it is
+// deferred to kernel 2, where every candidate gets its own warp.
+__device__ __forceinline__ void setup_img(Img &im, const Dims &d, int img, const LsdWord *lsdw, const LsdPix *pix, const u32 *pixxy,
+                                          u8 *used, u32 *reg, const int *pixcount)
 {
-    __shared__ u32 hist[1024];
-    __shared__ Seq3 sm;
-    const int img = blockIdx.x, lane = threadIdx.x;
-    Img im;
     im.n = pixcount[img];
     im.W = d.sw; im.H = d.sh; im.swp = d.swp;
     im.words = lsdw + (size_t)img * d.sh * d.swp;
@@ -502,10 +509,24 @@ __global__ void __launch_bounds__(32) k_lsd_core(Dims d, const LsdWord *__restri
     im.used = used + (size_t)img * d.pixcap;
     im.reg = reg + (size_t)img * 2 * d.pixcap;   // second half: scratch of reduce_region_radius
     im.cap = d.pixcap;
+    im.logNT = 5.0 * (log10((double)im.W) + log10((double)im.H)) / 2.0 + log10(11.0);
+}
+
+__global__ void __launch_bounds__(32) k_lsd_grow(Dims d, const LsdWord *__restrict__ lsdw, const LsdPix *__restrict__ pix,
+                                                const u32 *__restrict__ pixxy, u8 *__restrict__ used, u32 *__restrict__ order,
+                                                u32 *__restrict__ reg, const int *__restrict__ pixcount,
+                                                const u32 *__restrict__ g2max, LsdCand *__restrict__ cand,
+                                                int *__restrict__ candcount, uint2 *__restrict__ candlist, int *__restrict__ flags)
+{
+    __shared__ u32 hist[1024];
+    __shared__ Seq3 sm;
+    const int img = blockIdx.x, lane = threadIdx.x;
+    Img im;
+    setup_img(im, d, img, lsdw, pix, pixxy, used, reg, pixcount);
     u32 *ord = order + (size_t)img * d.pixcap;
     const int n = im.n;
     if (n == 0) {
-        if (lane == 0) segcount[img] = 0;
+        if (lane == 0) candcount[img] = 0;
         return;
     }
     // ---- seed order: stable counting sort by bin = int(norm * 1023 / max_norm), descending ----
@@ -550,10 +571,9 @@ __global__ void __launch_bounds__(32) k_lsd_core(Dims d, const LsdWord *__restri
 
     // ---- search ----
     const double prec = kPI * 22.5 / 180.0, p = 22.5 / 180.0;
-    im.logNT = 5.0 * (log10((double)im.W) + log10((double)im.H)) / 2.0 + log10(11.0);
     const int min_reg = (int)(-im.logNT / log10(p));
-    int nout = 0;
-    LsdSeg *out = rawseg + (size_t)img * d.segcap;
+    int ncand = 0;
+    LsdCand *out = cand + (size_t)img * d.segcap;
     for (int o0 = 0; o0 < n; o0 += 32) {
         int oi = o0 + lane;
         int ci = oi < n ? (int)ord[oi] : -1;
@@ -561,50 +581,109 @@ __global__ void __launch_bounds__(32) k_lsd_core(Dims d, const LsdWord *__restri
         while (true) {
             // seeds of this batch not yet visited and still unused *now* (refine may have released pixels)
             __syncwarp();
-            u32 cand = __ballot_sync(FULL, ci >= 0 && lane > k && im.used[ci] == 0);
-            if (!cand) break;
-            k = __ffs(cand) - 1;
+            u32 cnd = __ballot_sync(FULL, ci >= 0 && lane > k && im.used[ci] == 0);
+            if (!cnd) break;
+            k = __ffs(cnd) - 1;
             int seed = __shfl_sync(FULL, ci, k);
             double reg_angle;
             int nreg = grow(im, seed, prec, reg_angle);
             if (nreg < min_reg) continue;
             Rect rec;
             region2rect(im, sm, nreg, reg_angle, prec, p, rec);
-            const int nreg0 = nreg;
-            if (!refine(im, sm, nreg, reg_angle, prec, p, rec)) {
-                if (d.debug && lane == 0) printf("img %d cand seed=(%d,%d) refine-rejected nreg=%d nreg0=%d\n", img, im.xy[seed] & 0xffff, im.xy[seed] >> 16, nreg, nreg0);
-                continue;
+            if (!refine(im, sm, nreg, reg_angle, prec, p, rec)) continue;
+            if (ncand < d.segcap && lane == 0) {
+                LsdCand c;
+                c.x1 = rec.x1; c.y1 = rec.y1; c.x2 = rec.x2; c.y2 = rec.y2;
+                c.width = rec.width; c.theta = rec.theta; c.dx = rec.dx; c.dy = rec.dy;
+                out[ncand] = c;
+                int slot = atomicAdd(&flags[3], 1);
+                candlist[slot] = make_uint2((u32)img, (u32)ncand);
             }
-            double log_nfa = rect_improve(im, rec);
-            if (d.debug && lane == 0)
-                printf("img %d cand seed=(%d,%d) nreg=%d nreg0=%d nfa=%.17g p=%g w=%g (%.3f,%.3f)-(%.3f,%.3f)\n", img, im.xy[seed] & 0xffff,
-                       im.xy[seed] >> 16, nreg, nreg0, log_nfa, rec.p, rec.width, rec.x1, rec.y1, rec.x2, rec.y2);
-            if (d.debug > 1) rect_nfa(im, rec, true);
-            if (!(log_nfa > 0.0)) continue;
-            if (nout < d.segcap && lane == 0) {
-                LsdSeg s;
-                s.x1 = (float)((rec.x1 + 0.5) / 0.8); s.y1 = (float)((rec.y1 + 0.5) / 0.8);
-                s.x2 = (float)((rec.x2 + 0.5) / 0.8); s.y2 = (float)((rec.y2 + 0.5) / 0.8);
-                out[nout] = s;
-            }
-            ++nout;
+            ++ncand;
         }
     }
     if (lane == 0) {
-        if (nout > d.segcap) { atomicMax(&flags[1], nout); nout = d.segcap; }
-        segcount[img] = nout;
+        if (ncand > d.segcap) { atomicMax(&flags[1], ncand); ncand = d.segcap; }
+        candcount[img] = ncand;
     }
+}
+
+// ---- kernel 2: NFA validation with LSD_REFINE_ADV rectangle improvement, one warp per candidate ---------------
+constexpr int VAL_WARPS = 4;
+
+__global__ void __launch_bounds__(VAL_WARPS * 32) k_lsd_validate(Dims d, const LsdWord *__restrict__ lsdw, const LsdPix *__restrict__ pix,
+                                                                const int *__restrict__ pixcount, const LsdCand *__restrict__ cand,
+                                                                const uint2 *__restrict__ candlist, const int *__restrict__ flags,
+                                                                LsdSeg *__restrict__ candseg, u8 *__restrict__ candok)
+{
+    const int lane = threadIdx.x & 31;
+    const int total = min(flags[3], d.n * 3 * d.segcap);
+    const int nwarps = gridDim.x * VAL_WARPS;
+    for (int t = blockIdx.x * VAL_WARPS + (threadIdx.x >> 5); t < total; t += nwarps) {
+        uint2 e = candlist[t];
+        const int img = (int)e.x, ci = (int)e.y;
+        Img im;
+        setup_img(im, d, img, lsdw, pix, nullptr, nullptr, nullptr, pixcount);
+        const size_t o = (size_t)img * d.segcap + ci;
+        LsdCand c = cand[o];
+        Rect rec;
+        rec.x1 = c.x1; rec.y1 = c.y1; rec.x2 = c.x2; rec.y2 = c.y2; rec.width = c.width; rec.theta = c.theta;
+        rec.dx = c.dx; rec.dy = c.dy; rec.x = 0; rec.y = 0;
+        rec.prec = kPI * 22.5 / 180.0; rec.p = 22.5 / 180.0;
+        double log_nfa = rect_improve(im, rec);
+        if (d.debug && lane == 0)
+            printf("img %d cand %d nfa=%.17g p=%g w=%g (%.3f,%.3f)-(%.3f,%.3f)\n", img, ci, log_nfa, rec.p, rec.width, rec.x1, rec.y1,
+                   rec.x2, rec.y2);
+        if (lane == 0) {
+            LsdSeg sg;
+            sg.x1 = (float)((rec.x1 + 0.5) / 0.8); sg.y1 = (float)((rec.y1 + 0.5) / 0.8);
+            sg.x2 = (float)((rec.x2 + 0.5) / 0.8); sg.y2 = (float)((rec.y2 + 0.5) / 0.8);
+            candseg[o] = sg;
+            candok[o] = log_nfa > 0.0 ? 1 : 0;
+        }
+    }
+}
+
+// ---- kernel 3: keep the validated candidates, in candidate (= acceptance) order ------------------------------------
+__global__ void __launch_bounds__(128) k_lsd_emit(Dims d, const int *__restrict__ candcount, const LsdSeg *__restrict__ candseg,
+                                                 const u8 *__restrict__ candok, LsdSeg *__restrict__ rawseg, int *__restrict__ segcount)
+{
+    const int lane = threadIdx.x & 31;
+    const int img = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (img >= d.n * 3) return;
+    const int nc = candcount[img];
+    const size_t base = (size_t)img * d.segcap;
+    int nout = 0;
+    for (int i0 = 0; i0 < nc; i0 += 32) {
+        int i = i0 + lane;
+        bool ok = i < nc && candok[base + i];
+        u32 m = __ballot_sync(FULL, ok);
+        if (ok) rawseg[base + nout + __popc(m & ((1u << lane) - 1u))] = candseg[base + i];
+        nout += __popc(m);
+    }
+    if (lane == 0) segcount[img] = nout;
 }
 
 void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st)
 {
     static bool tab_ready = false;
+    static double *d_lgtab = nullptr;
     if (!tab_ready) {
         cudaMemcpyToSymbol(c_sincos_tab, scr::kSinCosTab, sizeof(scr::kSinCosTab));
+        std::vector<double> tab(LGTAB);
+        tab[0] = 0.0;
+        for (int i = 1; i < LGTAB; ++i) tab[i] = log_gamma_d((double)i);
+        cudaMalloc((void **)&d_lgtab, LGTAB * sizeof(double));
+        cudaMemcpy(d_lgtab, tab.data(), LGTAB * sizeof(double), cudaMemcpyHostToDevice);
+        cudaMemcpyToSymbol(g_lgtab, &d_lgtab, sizeof(d_lgtab));
         tab_ready = true;
     }
-    k_lsd_core<<<d.n * 3, 32, 0, st>>>(d, b.lsdw, b.pix, b.pixxy, b.used, b.order, b.reg, b.pixcount, b.g2max, b.rawseg,
-                                       b.segcount, b.flags);
+    k_lsd_grow<<<d.n * 3, 32, 0, st>>>(d, b.lsdw, b.pix, b.pixxy, b.used, b.order, b.reg, b.pixcount, b.g2max, b.cand, b.candcount,
+                                       b.candlist, b.flags);
+    ++g_launches;
+    k_lsd_validate<<<148 * 8, VAL_WARPS * 32, 0, st>>>(d, b.lsdw, b.pix, b.pixcount, b.cand, b.candlist, b.flags, b.candseg, b.candok);
+    ++g_launches;
+    k_lsd_emit<<<(d.n * 3 + 3) / 4, 128, 0, st>>>(d, b.candcount, b.candseg, b.candok, b.rawseg, b.segcount);
     ++g_launches;
 }
 

@@ -184,6 +184,11 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     CKC(dalloc(&b.pixcount, n * 3));
     CKC(dalloc(&b.g2max, n * 3));
     CKC(dalloc(&b.rawseg, n * 3 * ctx->segcap));
+    CKC(dalloc(&b.cand, n * 3 * ctx->segcap));
+    CKC(dalloc(&b.candcount, n * 3));
+    CKC(dalloc(&b.candlist, n * 3 * ctx->segcap));
+    CKC(dalloc(&b.candseg, n * 3 * ctx->segcap));
+    CKC(dalloc(&b.candok, n * 3 * ctx->segcap));
     CKC(dalloc(&b.segcount, n * 3));
     CKC(dalloc(&b.frame_off, (n + 1) + n * 3));
     CKC(dalloc(&b.flags, 4));
@@ -209,7 +214,7 @@ extern "C" void lsf_destroy(lsf_ctx *ctx)
     cudaSetDevice(ctx->device);
     Buffers &b = ctx->b;
     void *ptrs[] = {b.src, b.planesA, b.planesB, b.gray, b.dx, b.lsdw, b.pix, b.pixxy, b.used, b.order, b.reg, b.pixcount,
-                    b.g2max, b.rawseg, b.segcount, b.frame_off, b.flags, b.o_color, b.o_lines, b.o_normals, b.o_centers,
+                    b.g2max, b.rawseg, b.cand, b.candcount, b.candlist, b.candseg, b.candok, b.segcount, b.frame_off, b.flags, b.o_color, b.o_lines, b.o_normals, b.o_centers,
                     b.o_pixn, b.o_nf32, b.o_ground, b.o_keep, b.o_desc, b.o_frame, b.o_midx, b.o_mdist, ctx->map,
                     ctx->knn_scratch, ctx->tap_tmp, ctx->seg_in, ctx->carry};
     for (void *p : ptrs) if (p) cudaFree(p);
