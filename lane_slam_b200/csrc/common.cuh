@@ -103,7 +103,8 @@ void launch_color_canny(const Dims &d, const ColorParams &cp, const u8 *src, con
                         cudaStream_t st);
 void launch_hysteresis(const Dims &d, int dilate, const u32 *planesA, u32 *planesB, cudaStream_t st);
 void launch_lsd_pre(const Dims &d, const u32 *planesB, Buffers &b, cudaStream_t st);
-void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st);
+void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st);      // seeds + region growing + refine
+void launch_lsd_validate(const Dims &d, Buffers &b, cudaStream_t st);  // NFA validation + emit
 void launch_segments(const Dims &d, const CamParams &cam, Buffers &b, int do_ground, cudaStream_t st);
 void launch_gray_sobel(const Dims &d, const u8 *gray, short *dx, short *dy, cudaStream_t st);
 void launch_lbd(const Dims &d, const float *lines, const int *frame_of_seg, int nseg_cap, const int *nseg_dev,

@@ -681,6 +681,10 @@ void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st)
     k_lsd_grow<<<d.n * 3, 32, 0, st>>>(d, b.lsdw, b.pix, b.pixxy, b.used, b.order, b.reg, b.pixcount, b.g2max, b.cand, b.candcount,
                                        b.candlist, b.flags);
     ++g_launches;
+}
+
+void launch_lsd_validate(const Dims &d, Buffers &b, cudaStream_t st)
+{
     k_lsd_validate<<<148 * 8, VAL_WARPS * 32, 0, st>>>(d, b.lsdw, b.pix, b.pixcount, b.cand, b.candlist, b.flags, b.candseg, b.candok);
     ++g_launches;
     k_lsd_emit<<<(d.n * 3 + 3) / 4, 128, 0, st>>>(d, b.candcount, b.candseg, b.candok, b.rawseg, b.segcount);

@@ -1,19 +1,22 @@
 // k_lsd_pre.cu -- K6+K7(+K8 compaction): LSD pre-processing of one binary edge_color image:
-// 7x7 fixed-point Gaussian (sigma 0.75), 0.8x INTER_LINEAR_EXACT resize, 2x2 gradient, level-line
-// angle (fastAtan2), "defined" test, raster-ordered compaction of the support pixels.
+// 7x7 fixed-point Gaussian (sigma 0.75; effective taps 4,56,136,56,4), 0.8x INTER_LINEAR_EXACT resize,
+// 2x2 gradient, level-line angle (fastAtan2), "defined" test, raster-ordered compaction of support pixels.
 //
 // Replaces the first half of cv2.LineSegmentDetector.detect (line_detector_lsd.py:64-67):
 // GaussianBlur + resize + ll_angle.  Input is a packed bit-plane (edge_color is
 // 0/255), so the source costs N/8 bytes; the output is sparse: one {bits, base} word per 32 scaled
 // pixels plus one 16-byte record per support pixel (0.3-3 % of the pixels).
 //
-// One CTA per (frame, colour); the CTA walks the image in bands of 8 scaled rows, so the running
-// count of support pixels (= raster-order compact index) is known without a second pass.
+// One CTA per (frame, colour) walks the image in bands of 8 scaled rows, so the running count of support
+// pixels (= raster-order compact index) is known without a second pass.  Edges are sparse: per band the
+// CTA derives which 32-pixel column words can be non-zero at each stage (from the OR of the band's source
+// bit rows) and runs every stage only on those words; empty bands cost one load + one barrier.
 #include "common.cuh"
 
 namespace lsf {
 
 constexpr int PT = 256;   // threads
+constexpr int NW = PT / 32;
 constexpr int BR = 8;     // scaled rows per band
 constexpr int HZR = 16;   // horizontal-blur rows held per band (source rows s0-2 .. s0+13)
 constexpr int GR = 12;    // blurred rows per band (source rows s0 .. s0+11)
@@ -23,6 +26,23 @@ __device__ __forceinline__ int refl101(int i, int n)
     if (n == 1) return 0;
     while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
     return i;
+}
+
+__device__ __forceinline__ int tapw(int j) { return (j == 0) ? 136 : (j == 1 || j == -1) ? 56 : 4; }
+
+// compact the indices i in [0, n) with flag[i] != 0 into list[]; returns the count (call from one warp)
+__device__ __forceinline__ int warp_compact(const u8 *flag, int n, u16 *list)
+{
+    const int lane = threadIdx.x & 31;
+    int cnt = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        int i = i0 + lane;
+        bool f = i < n && flag[i];
+        u32 m = __ballot_sync(0xffffffffu, f);
+        if (f) list[cnt + __popc(m & ((1u << lane) - 1u))] = (u16)i;
+        cnt += __popc(m);
+    }
+    return cnt;
 }
 
 __global__ void __launch_bounds__(PT) k_lsd_pre(Dims d, u32 g2_min, const u32 *__restrict__ planesB, LsdWord *__restrict__ lsdw,
@@ -40,8 +60,15 @@ __global__ void __launch_bounds__(PT) k_lsd_pre(Dims d, u32 g2_min, const u32 *_
     u32 *sbits = (u32 *)(sc + (((size_t)(BR + 1) * sw + 3) & ~(size_t)3));  // [HZR][wp]
     u32 *wbits = sbits + (size_t)HZR * wp;             // [BR*swp]
     u32 *wbase = wbits + (size_t)BR * swp;             // [BR*swp]
-    __shared__ u32 s_run, s_warp_tot[PT / 32];
-    __shared__ u32 s_gmax;
+    u16 *listG = (u16 *)(wbase + (size_t)BR * swp);    // [wp]   source words needed by the blur stages
+    u16 *listS = listG + wp;                           // [swp]  scaled words needed by the resize stage
+    u16 *listD = listS + swp;                          // [swp]  scaled words that may hold support pixels
+    u8 *actS = (u8 *)(listD + swp);                    // [wp]   source word has an edge bit in this band
+    u8 *needG = actS + wp;                             // [wp]
+    u8 *actD = needG + wp;                             // [swp]
+    u8 *needS = actD + swp;                            // [swp]
+    __shared__ u32 s_run, s_warp_tot[NW], s_gmax;
+    __shared__ int s_nG, s_nS, s_nD;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     LsdWord *ow = lsdw + (size_t)img * sh * swp;
@@ -50,74 +77,114 @@ __global__ void __launch_bounds__(PT) k_lsd_pre(Dims d, u32 g2_min, const u32 *_
     u8 *oused = used + (size_t)img * d.pixcap;
     if (tid == 0) { s_run = 0; s_gmax = 0; }
     u32 my_gmax = 0;
+    const int wlast = (w - 1) >> 5;   // source word holding the last image column
     __syncthreads();
 
     for (int ys0 = 0; ys0 < sh; ys0 += BR) {
         const int s0 = ys0 + (ys0 >> 2);           // first source row of the band
         const int hz_lo = s0 - 2;                  // source row held in hz slot 0
-        // ---- load source bit rows; detect an empty band ----
+        const int band_rows = min(BR, sh - ys0);
+        const int ntask = band_rows * swp;
+        // ---- load the band's source bit rows; column activity ----
+        for (int i = tid; i < wp; i += PT) { actS[i] = 0; needG[i] = 0; }
+        for (int i = tid; i < swp; i += PT) { actD[i] = 0; needS[i] = 0; }
+        __syncthreads();
         int nz = 0;
         for (int i = tid; i < HZR * wp; i += PT) {
-            int r = i / wp, yy = hz_lo + r;
-            u32 v = (yy >= 0 && yy < h) ? src[(size_t)yy * wp + (i - r * wp)] : 0u;
+            int r = i / wp, xw = i - r * wp, yy = hz_lo + r;
+            u32 v = (yy >= 0 && yy < h) ? src[(size_t)yy * wp + xw] : 0u;
             sbits[i] = v;
-            nz |= v != 0;
+            if (v) { actS[xw] = 1; nz = 1; }
         }
         nz = __syncthreads_or(nz);
-        const int band_rows = min(BR, sh - ys0);
         if (!nz) {
             u32 run = s_run;
-            for (int i = tid; i < band_rows * swp; i += PT) ow[(size_t)ys0 * swp + i] = LsdWord{0u, run};
+            for (int i = tid; i < ntask; i += PT) ow[(size_t)ys0 * swp + i] = LsdWord{0u, run};
             continue;
         }
-        // ---- horizontal blur taps [4,56,136,56,4] on bits (reflect-101), value/255 in Q8 ----
-        for (int i = tid; i < HZR * w; i += PT) {
-            int r = i / w, x = i - r * w;
+        // scaled word xsw can be non-zero only if a source bit lies in columns [40 xsw - 2, 40 xsw + 43]
+        for (int xsw = tid; xsw < swp; xsw += PT) {
+            int wlo = max(0, (40 * xsw - 2) >> 5), whi = min(wp - 1, (40 * xsw + 43) >> 5);
+            int a = 0;
+            for (int k = wlo; k <= whi; ++k) a |= actS[k];
+            if (a) {
+                actD[xsw] = 1;
+                needS[xsw] = 1;
+                if (xsw + 1 < swp) needS[xsw + 1] = 1;   // right neighbour of lane 31
+            }
+        }
+        __syncthreads();
+        for (int xsw = tid; xsw < swp; xsw += PT) {
+            if (needS[xsw]) {
+                int wlo = (40 * xsw) >> 5, whi = min(wp - 1, (40 * xsw + 40) >> 5);
+                for (int k = wlo; k <= whi; ++k) needG[k] = 1;
+            }
+        }
+        __syncthreads();
+        if (warp == 0) { int nG = warp_compact(needG, wp, listG); if (lane == 0) s_nG = nG; }
+        if (warp == 1) { int nS = warp_compact(needS, swp, listS); if (lane == 0) s_nS = nS; }
+        if (warp == 2) { int nD = warp_compact(actD, swp, listD); if (lane == 0) s_nD = nD; }
+        for (int i = tid; i < ntask; i += PT) { wbits[i] = 0; wbase[i] = 0; }
+        __syncthreads();
+        const int nG = s_nG, nS = s_nS, nD = s_nD;
+
+        // ---- horizontal blur on bits (taps 4,56,136,56,4; reflect-101), value/255 in Q8 ----
+        for (int t = warp; t < HZR * nG; t += NW) {
+            int r = t / nG, xw = listG[t - r * nG], x = xw * 32 + lane;
             const u32 *row = sbits + r * wp;
             int acc = 0;
+            if (xw > 0 && xw * 32 + 33 < w) {
+                // interior word: 36-bit window = 2 bits of the left word | this word | 2 bits of the right word
+                unsigned long long win = ((unsigned long long)row[xw] << 2) | (row[xw - 1] >> 30) |
+                                         ((unsigned long long)(row[xw + 1] & 3u) << 34);
+                u32 v = (u32)(win >> lane) & 31u;   // bit j <-> column x - 2 + j
+                acc = 4 * (int)((v & 1u) + ((v >> 4) & 1u)) + 56 * (int)(((v >> 1) & 1u) + ((v >> 3) & 1u)) + 136 * (int)((v >> 2) & 1u);
+            } else if (x < w) {
 #pragma unroll
-            for (int j = -2; j <= 2; ++j) {
-                int xx = refl101(x + j, w);
-                int q = (j == 0) ? 136 : (j == 1 || j == -1) ? 56 : 4;
-                acc += q * (int)((row[xx >> 5] >> (xx & 31)) & 1u);
+                for (int j = -2; j <= 2; ++j) {
+                    int xx = refl101(x + j, w);
+                    acc += tapw(j) * (int)((row[xx >> 5] >> (xx & 31)) & 1u);
+                }
             }
-            hz[i] = (u16)acc;
+            if (x < w) hz[r * w + x] = (u16)acc;
         }
         __syncthreads();
         // ---- vertical blur -> g (u8) for source rows s0 .. s0+GR-1 (clamped to h-1) ----
-        for (int i = tid; i < GR * w; i += PT) {
-            int r = i / w, x = i - r * w;
-            int gy = min(s0 + r, h - 1);
-            int acc = 0;
+        for (int t = warp; t < GR * nG; t += NW) {
+            int r = t / nG, x = listG[t - r * nG] * 32 + lane;
+            if (x < w) {
+                int gy = min(s0 + r, h - 1);
+                int acc = 0;
 #pragma unroll
-            for (int j = -2; j <= 2; ++j) {
-                int yy = refl101(gy + j, h);
-                int q = (j == 0) ? 136 : (j == 1 || j == -1) ? 56 : 4;
-                acc += q * (int)hz[(yy - hz_lo) * w + x];
+                for (int j = -2; j <= 2; ++j) {
+                    int yy = refl101(gy + j, h);
+                    acc += tapw(j) * (int)hz[(yy - hz_lo) * w + x];
+                }
+                g[r * w + x] = (u8)((acc * 255 + 32768) >> 16);
             }
-            g[i] = (u8)((acc * 255 + 32768) >> 16);
         }
         __syncthreads();
         // ---- 0.8x bilinear (INTER_LINEAR_EXACT) -> scaled rows ys0 .. ys0+BR ----
-        for (int i = tid; i < (BR + 1) * sw; i += PT) {
-            int rs = i / sw, xs = i - rs * sw, ys = ys0 + rs;
-            u8 val = 0;
-            if (ys < sh) {
-                int sy = ys + (ys >> 2), sx = xs + (xs >> 2);
-                int ay = 32 + 64 * (ys & 3), ax = 32 + 64 * (xs & 3);
-                int r0 = min(sy, h - 1) - s0, r1 = min(sy + 1, h - 1) - s0;
-                int x0 = min(sx, w - 1), x1 = min(sx + 1, w - 1);
-                int h0 = g[r0 * w + x0] * (256 - ax) + g[r0 * w + x1] * ax;
-                int h1 = g[r1 * w + x0] * (256 - ax) + g[r1 * w + x1] * ax;
-                val = (u8)((h0 * (256 - ay) + h1 * ay + 32768) >> 16);
+        for (int t = warp; t < (BR + 1) * nS; t += NW) {
+            int rs = t / nS, xs = listS[t - rs * nS] * 32 + lane, ys = ys0 + rs;
+            if (xs < sw) {
+                u8 val = 0;
+                if (ys < sh) {
+                    int sy = ys + (ys >> 2), sx = xs + (xs >> 2);
+                    int ay = 32 + 64 * (ys & 3), ax = 32 + 64 * (xs & 3);
+                    int r0 = min(sy, h - 1) - s0, r1 = min(sy + 1, h - 1) - s0;
+                    int x0 = min(sx, w - 1), x1 = min(sx + 1, w - 1);
+                    int h0 = g[r0 * w + x0] * (256 - ax) + g[r0 * w + x1] * ax;
+                    int h1 = g[r1 * w + x0] * (256 - ax) + g[r1 * w + x1] * ax;
+                    val = (u8)((h0 * (256 - ay) + h1 * ay + 32768) >> 16);
+                }
+                sc[rs * sw + xs] = val;
             }
-            sc[i] = val;
         }
         __syncthreads();
-        // ---- gradient / defined bits: warp task = (row, word) ----
-        const int ntask = band_rows * swp;
-        for (int t = warp; t < ntask; t += PT / 32) {
-            int rs = t / swp, xw = t - rs * swp, xs = xw * 32 + lane, ys = ys0 + rs;
+        // ---- gradient / defined bits on the active words ----
+        for (int t = warp; t < band_rows * nD; t += NW) {
+            int rs = t / nD, xw = listD[t - rs * nD], xs = xw * 32 + lane, ys = ys0 + rs;
             bool def = false;
             if (xs < sw - 1 && ys < sh - 1) {
                 const u8 *r0 = sc + rs * sw + xs, *r1 = r0 + sw;
@@ -127,13 +194,12 @@ __global__ void __launch_bounds__(PT) k_lsd_pre(Dims d, u32 g2_min, const u32 *_
                 def = g2 >= g2_min;
             }
             u32 bits = __ballot_sync(0xffffffffu, def);
-            if (lane == 0) { wbits[t] = bits; wbase[t] = __popc(bits); }
+            if (lane == 0) { wbits[rs * swp + xw] = bits; wbase[rs * swp + xw] = __popc(bits); }
         }
         __syncthreads();
-        // ---- exclusive scan of the per-word counts over the band (ntask <= a few hundred) ----
+        // ---- exclusive scan of the per-word counts over the band ----
         {
             u32 run = s_run;
-            // each thread owns a contiguous chunk
             int per = (ntask + PT - 1) / PT;
             int b0 = tid * per, b1 = min(ntask, b0 + per);
             u32 sum = 0;
@@ -154,11 +220,11 @@ __global__ void __launch_bounds__(PT) k_lsd_pre(Dims d, u32 g2_min, const u32 *_
             if (tid == PT - 1) s_run = excl;   // last thread ends at the band total
         }
         __syncthreads();
-        // ---- write words + compact records ----
-        for (int t = warp; t < ntask; t += PT / 32) {
-            int rs = t / swp, xw = t - rs * swp, xs = xw * 32 + lane, ys = ys0 + rs;
-            u32 bits = wbits[t], base = wbase[t];
-            if (lane == 0) ow[(size_t)ys * swp + xw] = LsdWord{bits, base};
+        // ---- words of the band, then the compact records of the active words ----
+        for (int i = tid; i < ntask; i += PT) ow[(size_t)ys0 * swp + i] = LsdWord{wbits[i], wbase[i]};
+        for (int t = warp; t < band_rows * nD; t += NW) {
+            int rs = t / nD, xw = listD[t - rs * nD], xs = xw * 32 + lane, ys = ys0 + rs;
+            u32 bits = wbits[rs * swp + xw], base = wbase[rs * swp + xw];
             if ((bits >> lane) & 1u) {
                 u32 idx = base + __popc(bits & ((1u << lane) - 1u));
                 const u8 *r0 = sc + rs * sw + xs, *r1 = r0 + sw;
@@ -196,7 +262,7 @@ __global__ void __launch_bounds__(PT) k_lsd_pre(Dims d, u32 g2_min, const u32 *_
 static size_t lsd_pre_smem(const Dims &d)
 {
     size_t s = (size_t)HZR * d.w * 2 + (size_t)GR * d.w + (((size_t)(BR + 1) * d.sw + 3) & ~(size_t)3) +
-               (size_t)HZR * d.wp * 4 + (size_t)BR * d.swp * 8;
+               (size_t)HZR * d.wp * 4 + (size_t)BR * d.swp * 8 + (size_t)(d.wp + 2 * d.swp) * 2 + (size_t)(2 * d.wp + 2 * d.swp);
     return s + 16;
 }
 

@@ -380,7 +380,9 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
     launch_lsd_pre(d, b.planesB, b, ctx->st);
     mark(ctx, "lsd_pre");
     launch_lsd_core(d, b, ctx->st);
-    mark(ctx, "lsd_core");
+    mark(ctx, "lsd_grow");
+    launch_lsd_validate(d, b, ctx->st);
+    mark(ctx, "lsd_validate");
     launch_segments(d, ctx->cam, b, (stages & LSF_STAGE_GROUND) ? 1 : 0, ctx->st);
     mark(ctx, "segments");
     if (stages & LSF_STAGE_DESCRIBE) {
