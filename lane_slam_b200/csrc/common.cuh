@@ -40,12 +40,16 @@ struct Dims {
 // one entry per 32 scaled pixels: defined-angle bits + number of defined pixels before this word
 struct LsdWord { u32 bits; u32 base; };
 
-// per LSD support pixel (raster order inside one colour image)
-struct LsdPix {
-    float ang_deg;  // fastAtan2 result in degrees
-    float c, s;     // cosf / sinf of float(angle_rad)
+// per LSD support pixel (raster order inside one colour image), 32 bytes
+struct __align__(16) LsdPix {
+    double ang;     // level-line angle in radians: double(fastAtan2 degrees) * pi/180
+    float c, s;     // cosf / sinf of float(ang)
     u32 g2;         // gx^2 + gy^2 (norm = sqrt(g2/4))
+    u32 xy;         // (y << 16) | x in the scaled image
+    u32 used;       // region-growing USED flag
+    u32 pad;
 };
+constexpr u32 LSD_NONE = 0xffffffffu;
 
 // parameters handed to kernels by value
 struct ColorParams {
@@ -75,8 +79,7 @@ struct Buffers {
     short *dx, *dy;     // [n][h][w]  (descriptor path)
     LsdWord *lsdw;      // [n*3][sh][swp]
     LsdPix *pix;        // [n*3][pixcap]
-    u32 *pixxy;         // [n*3][pixcap]  (y<<16 | x)
-    u8 *used;           // [n*3][pixcap]
+    u32 *nbr;           // [n*3][pixcap][8] compact indices of the 8 neighbours (row-major, centre skipped) or LSD_NONE
     u32 *order;         // [n*3][pixcap]  seed order (compact indices)
     u32 *reg;           // [n*3][2*pixcap] region point list + scratch
     int *pixcount;      // [n*3]

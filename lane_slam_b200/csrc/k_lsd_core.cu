@@ -28,9 +28,8 @@ struct Rect { double x1, y1, x2, y2, width, x, y, theta, dx, dy, prec, p; };
 
 struct Img {
     const LsdWord *words;
-    const LsdPix *pix;
-    const u32 *xy;
-    u8 *used;
+    LsdPix *pix;
+    const u32 *nbr;
     u32 *reg;
     int W, H, swp, n, cap;
     double logNT;
@@ -142,39 +141,43 @@ __device__ double nfa_d(int n, int k, double p, double logNT)
 // ---- region growing -----------------------------------------------------------------------------------
 // Grows from compact index `seed` with tolerance prec; fills im.reg[0..nreg) (acceptance order), marks
 // pixels used, returns nreg and the final region angle.
+//
+// The FIFO is consumed three points per round: lanes 0-8 / 9-17 / 18-26 hold the 3x3 neighbourhoods (row
+// major, centre idle) of three consecutive queue entries, fetched with one round trip (queue entry ->
+// neighbour table -> pixel record).  Acceptances are then resolved strictly in the reference's order: group
+// by group, neighbour by neighbour, the region angle updated after every accepted pixel.  A pixel accepted
+// earlier in the round is dropped from the later groups (it is USED by then in the reference as well).
 __device__ int grow(const Img &im, int seed, double prec, double &reg_angle_out)
 {
     const int lane = threadIdx.x & 31;
+    const int grp = lane / 9, slot = lane - 9 * grp;
+    const bool nb_lane = grp < 3 && slot != 4;
+    const int nslot = slot < 4 ? slot : slot - 1;
     int nreg = 1;
-    double reg_angle = (double)im.pix[seed].ang_deg * kDEG2RAD;
+    double reg_angle = im.pix[seed].ang;
     float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
-    if (lane == 0) { im.reg[0] = (u32)seed; im.used[seed] = 1; }
+    if (lane == 0) { im.reg[0] = (u32)seed; im.pix[seed].used = 1; }
     __syncwarp();
-    const int ddy = lane / 3 - 1, ddx = lane - (lane / 3) * 3 - 1;  // lanes 0..8: row-major 3x3
-    for (int i0 = 0, navail = 0; i0 < nreg; i0 += navail) {
-        // fetch up to 32 queued points at once (entries appended later are fetched by the next batch)
-        navail = min(32, nreg - i0);
-        u32 myp = lane < navail ? im.reg[i0 + lane] : 0u;
-        u32 myxy = lane < navail ? im.xy[myp] : 0u;
-        for (int j = 0; j < navail; ++j) {
-            u32 pxy = __shfl_sync(FULL, myxy, j);
-            int px = (int)(pxy & 0xffffu), py = (int)(pxy >> 16);
-            int xx = px + ddx, yy = py + ddy;
-            int idx = -1;
-            double ang = 0;
-            float c = 0, s = 0;
-            if (lane < 9 && xx >= 0 && xx < im.W && yy >= 0 && yy < im.H) {
-                idx = lookup(im, xx, yy);
-                if (idx >= 0) {
-                    if (im.used[idx]) idx = -1;
-                    else {
-                        LsdPix p = im.pix[idx];
-                        ang = (double)p.ang_deg * kDEG2RAD;
-                        c = p.c; s = p.s;
-                    }
+    for (int i = 0; i < nreg;) {
+        const int navail = min(3, nreg - i);
+        int idx = -1;
+        double ang = 0;
+        float c = 0, s = 0;
+        if (nb_lane && grp < navail) {
+            u32 p = im.reg[i + grp];
+            u32 ni = im.nbr[(size_t)p * 8 + nslot];
+            if (ni != LSD_NONE) {
+                const uint4 *rp = reinterpret_cast<const uint4 *>(&im.pix[ni]);
+                uint4 r0 = rp[0], r1 = rp[1];
+                if (r1.z == 0) {   // not USED
+                    idx = (int)ni;
+                    ang = __hiloint2double((int)r0.y, (int)r0.x);
+                    c = __uint_as_float(r0.z); s = __uint_as_float(r0.w);
                 }
             }
-            u32 pending = __ballot_sync(FULL, idx >= 0);
+        }
+        for (int g = 0; g < navail; ++g) {
+            u32 pending = __ballot_sync(FULL, idx >= 0) & (0x1ffu << (9 * g));
             while (pending) {
                 bool al = idx >= 0 && aligned_ang(ang, reg_angle, prec);
                 u32 m = __ballot_sync(FULL, al) & pending;
@@ -182,7 +185,8 @@ __device__ int grow(const Img &im, int seed, double prec, double &reg_angle_out)
                 int k = __ffs(m) - 1;
                 int idxk = __shfl_sync(FULL, idx, k);
                 float ck = __shfl_sync(FULL, c, k), sk = __shfl_sync(FULL, s, k);
-                if (lane == k) { im.used[idx] = 1; idx = -1; }
+                if (lane == k) im.pix[idx].used = 1;
+                if (idx == idxk) idx = -1;          // the accepted lane and its duplicates in later groups
                 if (lane == 0) im.reg[nreg] = (u32)idxk;
                 ++nreg;
                 sumdx = __fadd_rn(sumdx, ck);
@@ -190,8 +194,9 @@ __device__ int grow(const Img &im, int seed, double prec, double &reg_angle_out)
                 reg_angle = (double)fast_atan2_deg(sumdy, sumdx) * kDEG2RAD;
                 pending &= ~((2u << k) - 1u);
             }
-            __syncwarp();  // used[] / reg[] writes of this point are visible to the next one
         }
+        __syncwarp();  // used / reg writes of this round are visible to the next one
+        i += navail;
     }
     reg_angle_out = reg_angle;
     return nreg;
@@ -222,7 +227,7 @@ __device__ void region2rect(const Img &im, Seq3 &sm, int nreg, double reg_angle,
         double tx = 0, ty = 0, tw = 0;
         if (i < nreg) {
             u32 q = im.reg[i];
-            u32 xy = im.xy[q];
+            u32 xy = im.pix[q].xy;
             tw = sqrt((double)im.pix[q].g2 / 4.0);
             tx = (double)(xy & 0xffffu) * tw;
             ty = (double)(xy >> 16) * tw;
@@ -236,7 +241,7 @@ __device__ void region2rect(const Img &im, Seq3 &sm, int nreg, double reg_angle,
         double ta = 0, tb = 0, tc = 0;
         if (i < nreg) {
             u32 q = im.reg[i];
-            u32 xy = im.xy[q];
+            u32 xy = im.pix[q].xy;
             double w = sqrt((double)im.pix[q].g2 / 4.0);
             double dx = (double)(xy & 0xffffu) - x, dy = (double)(xy >> 16) - y;
             ta = dy * dy * w; tb = dx * dx * w; tc = -(dx * dy * w);   // Ixy -= dx*dy*w
@@ -254,7 +259,7 @@ __device__ void region2rect(const Img &im, Seq3 &sm, int nreg, double reg_angle,
     // extents: min / max are order independent
     double lmin = 0, lmax = 0, wmn = 0, wmx = 0;
     for (int i = lane; i < nreg; i += 32) {
-        u32 xy = im.xy[im.reg[i]];
+        u32 xy = im.pix[im.reg[i]].xy;
         double rdx = (double)(xy & 0xffffu) - x, rdy = (double)(xy >> 16) - y;
         double l = rdx * dx + rdy * dy, w = -rdx * dy + rdy * dx;
         lmax = fmax(lmax, l); lmin = fmin(lmin, l);
@@ -279,20 +284,20 @@ __device__ bool refine(const Img &im, Seq3 &sm, int &nreg, double &reg_angle, do
     const int lane = threadIdx.x & 31;
     if (rect_density(nreg, rec) >= density_th) return true;
     const int seed = (int)im.reg[0];
-    const u32 sxy = im.xy[seed];
+    const u32 sxy = im.pix[seed].xy;
     const double xc = (double)(sxy & 0xffffu), yc = (double)(sxy >> 16);
-    const double ang_c = (double)im.pix[seed].ang_deg * kDEG2RAD;
+    const double ang_c = im.pix[seed].ang;
     double sum = 0, s_sum = 0, cnt = 0;
     for (int i0 = 0; i0 < nreg; i0 += 32) {
         int i = i0 + lane;
         double ta = 0, tb = 0, tc = 0;
         if (i < nreg) {
             u32 q = im.reg[i];
-            im.used[q] = 0;
-            u32 xy = im.xy[q];
+            im.pix[q].used = 0;
+            u32 xy = im.pix[q].xy;
             double ex = (double)(xy & 0xffffu) - xc, ey = (double)(xy >> 16) - yc;
             if (sqrt(ex * ex + ey * ey) < rec.width) {
-                double ad = angle_diff_signed((double)im.pix[q].ang_deg * kDEG2RAD, ang_c);
+                double ad = angle_diff_signed(im.pix[q].ang, ang_c);
                 ta = ad; tb = ad * ad; tc = 1.0;
             }
         }
@@ -322,10 +327,10 @@ __device__ bool refine(const Img &im, Seq3 &sm, int &nreg, double &reg_angle, do
                 bool keep = false;
                 if (i < nreg) {
                     u32 q = im.reg[i];
-                    u32 xy = im.xy[q];
+                    u32 xy = im.pix[q].xy;
                     double ex = xc - (double)(xy & 0xffffu), ey = yc - (double)(xy >> 16);
                     keep = !(ex * ex + ey * ey > radSq);
-                    if (!keep) im.used[q] = 0;
+                    if (!keep) im.pix[q].used = 0;
                 }
                 K += __popc(__ballot_sync(FULL, keep));
             }
@@ -337,7 +342,7 @@ __device__ bool refine(const Img &im, Seq3 &sm, int &nreg, double &reg_angle, do
                 bool keep = false;
                 if (i < nreg) {
                     q = im.reg[i];
-                    u32 xy = im.xy[q];
+                    u32 xy = im.pix[q].xy;
                     double ex = xc - (double)(xy & 0xffffu), ey = yc - (double)(xy >> 16);
                     keep = !(ex * ex + ey * ey > radSq);
                 }
@@ -352,7 +357,7 @@ __device__ bool refine(const Img &im, Seq3 &sm, int &nreg, double &reg_angle, do
                 int i = i0 + lane;
                 bool keep = true;
                 if (i < K) {
-                    u32 xy = im.xy[im.reg[i]];
+                    u32 xy = im.pix[im.reg[i]].xy;
                     double ex = xc - (double)(xy & 0xffffu), ey = yc - (double)(xy >> 16);
                     keep = !(ex * ex + ey * ey > radSq);
                 }
@@ -440,7 +445,7 @@ __device__ double rect_nfa(const Img &im, const Rect &r, bool verbose = false)
             if (t < T) {
                 int x = r_xa + (t - (r_incl - r_cnt));
                 int idx = lookup(im, x, y0 + lo);
-                if (idx >= 0 && aligned_ang((double)im.pix[idx].ang_deg * kDEG2RAD, r.theta, r.prec)) ++alg;
+                if (idx >= 0 && aligned_ang(im.pix[idx].ang, r.theta, r.prec)) ++alg;
             }
         }
     }
@@ -498,22 +503,48 @@ __device__ double rect_improve(const Img &im, Rect &rec)
 // One warp per (frame, colour) image; strictly sequential in the reference's seed order because growing and
 // refining change which pixels later seeds may use.  NFA validation does not touch that state, so it is
 // deferred to kernel 2, where every candidate gets its own warp.
-__device__ __forceinline__ void setup_img(Img &im, const Dims &d, int img, const LsdWord *lsdw, const LsdPix *pix, const u32 *pixxy,
-                                          u8 *used, u32 *reg, const int *pixcount)
+__device__ __forceinline__ void setup_img(Img &im, const Dims &d, int img, const LsdWord *lsdw, LsdPix *pix, const u32 *nbr,
+                                          u32 *reg, const int *pixcount)
 {
     im.n = pixcount[img];
     im.W = d.sw; im.H = d.sh; im.swp = d.swp;
     im.words = lsdw + (size_t)img * d.sh * d.swp;
     im.pix = pix + (size_t)img * d.pixcap;
-    im.xy = pixxy + (size_t)img * d.pixcap;
-    im.used = used + (size_t)img * d.pixcap;
-    im.reg = reg + (size_t)img * 2 * d.pixcap;   // second half: scratch of reduce_region_radius
+    im.nbr = nbr ? nbr + (size_t)img * d.pixcap * 8 : nullptr;
+    im.reg = reg ? reg + (size_t)img * 2 * d.pixcap : nullptr;   // second half: scratch of reduce_region_radius
     im.cap = d.pixcap;
     im.logNT = 5.0 * (log10((double)im.W) + log10((double)im.H)) / 2.0 + log10(11.0);
 }
 
-__global__ void __launch_bounds__(32) k_lsd_grow(Dims d, const LsdWord *__restrict__ lsdw, const LsdPix *__restrict__ pix,
-                                                const u32 *__restrict__ pixxy, u8 *__restrict__ used, u32 *__restrict__ order,
+// ---- kernel 0: 8-neighbour table of the support pixels (fully parallel) ------------------------------------------
+__global__ void __launch_bounds__(256) k_lsd_nbr(Dims d, const LsdWord *__restrict__ lsdw, const LsdPix *__restrict__ pix,
+                                                const int *__restrict__ pixcount, u32 *__restrict__ nbr)
+{
+    const int img = blockIdx.x;
+    Img im;
+    setup_img(im, d, img, lsdw, const_cast<LsdPix *>(pix), nullptr, nullptr, pixcount);
+    uint4 *out = reinterpret_cast<uint4 *>(nbr + (size_t)img * d.pixcap * 8);
+    for (int i = threadIdx.x; i < im.n; i += 256) {
+        u32 xy = im.pix[i].xy;
+        int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
+        u32 v[8];
+        int k = 0;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                if (dx == 0 && dy == 0) continue;
+                int xx = x + dx, yy = y + dy, r = -1;
+                if (xx >= 0 && xx < im.W && yy >= 0 && yy < im.H) r = lookup(im, xx, yy);
+                v[k++] = r >= 0 ? (u32)r : LSD_NONE;
+            }
+        out[2 * (size_t)i] = make_uint4(v[0], v[1], v[2], v[3]);
+        out[2 * (size_t)i + 1] = make_uint4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+__global__ void __launch_bounds__(32) k_lsd_grow(Dims d, const LsdWord *__restrict__ lsdw, LsdPix *__restrict__ pix,
+                                                const u32 *__restrict__ nbr, u32 *__restrict__ order,
                                                 u32 *__restrict__ reg, const int *__restrict__ pixcount,
                                                 const u32 *__restrict__ g2max, LsdCand *__restrict__ cand,
                                                 int *__restrict__ candcount, uint2 *__restrict__ candlist, int *__restrict__ flags)
@@ -522,7 +553,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow(Dims d, const LsdWord *__restri
     __shared__ Seq3 sm;
     const int img = blockIdx.x, lane = threadIdx.x;
     Img im;
-    setup_img(im, d, img, lsdw, pix, pixxy, used, reg, pixcount);
+    setup_img(im, d, img, lsdw, pix, nbr, reg, pixcount);
     u32 *ord = order + (size_t)img * d.pixcap;
     const int n = im.n;
     if (n == 0) {
@@ -581,7 +612,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow(Dims d, const LsdWord *__restri
         while (true) {
             // seeds of this batch not yet visited and still unused *now* (refine may have released pixels)
             __syncwarp();
-            u32 cnd = __ballot_sync(FULL, ci >= 0 && lane > k && im.used[ci] == 0);
+            u32 cnd = __ballot_sync(FULL, ci >= 0 && lane > k && im.pix[ci].used == 0);
             if (!cnd) break;
             k = __ffs(cnd) - 1;
             int seed = __shfl_sync(FULL, ci, k);
@@ -623,7 +654,7 @@ __global__ void __launch_bounds__(VAL_WARPS * 32) k_lsd_validate(Dims d, const L
         uint2 e = candlist[t];
         const int img = (int)e.x, ci = (int)e.y;
         Img im;
-        setup_img(im, d, img, lsdw, pix, nullptr, nullptr, nullptr, pixcount);
+        setup_img(im, d, img, lsdw, const_cast<LsdPix *>(pix), nullptr, nullptr, pixcount);
         const size_t o = (size_t)img * d.segcap + ci;
         LsdCand c = cand[o];
         Rect rec;
@@ -678,7 +709,9 @@ void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st)
         cudaMemcpyToSymbol(g_lgtab, &d_lgtab, sizeof(d_lgtab));
         tab_ready = true;
     }
-    k_lsd_grow<<<d.n * 3, 32, 0, st>>>(d, b.lsdw, b.pix, b.pixxy, b.used, b.order, b.reg, b.pixcount, b.g2max, b.cand, b.candcount,
+    k_lsd_nbr<<<d.n * 3, 256, 0, st>>>(d, b.lsdw, b.pix, b.pixcount, b.nbr);
+    ++g_launches;
+    k_lsd_grow<<<d.n * 3, 32, 0, st>>>(d, b.lsdw, b.pix, b.nbr, b.order, b.reg, b.pixcount, b.g2max, b.cand, b.candcount,
                                        b.candlist, b.flags);
     ++g_launches;
 }

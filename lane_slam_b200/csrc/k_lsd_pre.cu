@@ -46,7 +46,7 @@ __device__ __forceinline__ int warp_compact(const u8 *flag, int n, u16 *list)
 }
 
 __global__ void __launch_bounds__(PT) k_lsd_pre(Dims d, u32 g2_min, const u32 *__restrict__ planesB, LsdWord *__restrict__ lsdw,
-                                               LsdPix *__restrict__ pix, u32 *__restrict__ pixxy, u8 *__restrict__ used,
+                                               LsdPix *__restrict__ pix,
                                                int *__restrict__ pixcount, u32 *__restrict__ g2max, int *__restrict__ flags)
 {
     extern __shared__ __align__(16) u8 smraw[];
@@ -73,8 +73,6 @@ __global__ void __launch_bounds__(PT) k_lsd_pre(Dims d, u32 g2_min, const u32 *_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     LsdWord *ow = lsdw + (size_t)img * sh * swp;
     LsdPix *opix = pix + (size_t)img * d.pixcap;
-    u32 *oxy = pixxy + (size_t)img * d.pixcap;
-    u8 *oused = used + (size_t)img * d.pixcap;
     if (tid == 0) { s_run = 0; s_gmax = 0; }
     u32 my_gmax = 0;
     const int wlast = (w - 1) >> 5;   // source word holding the last image column
@@ -237,13 +235,14 @@ __global__ void __launch_bounds__(PT) k_lsd_pre(Dims d, u32 g2_min, const u32 *_
                     double ar = (double)a * (3.14159265358979323846 / 180.0);
                     float af = (float)ar;
                     LsdPix p;
-                    p.ang_deg = a;
+                    p.ang = ar;
                     p.c = (float)cos((double)af);   // cosf(float(angle)), correctly rounded
                     p.s = (float)sin((double)af);
                     p.g2 = g2;
+                    p.xy = ((u32)ys << 16) | (u32)xs;
+                    p.used = 0;
+                    p.pad = 0;
                     opix[idx] = p;
-                    oxy[idx] = ((u32)ys << 16) | (u32)xs;
-                    oused[idx] = 0;
                 }
             }
         }
@@ -278,7 +277,7 @@ void launch_lsd_pre(const Dims &d, const u32 *planesB, Buffers &b, cudaStream_t 
     const double rho = 2.0 / sin(3.14159265358979323846 * 22.5 / 180.0);
     u32 g2_min = 0;
     while (!(sqrt((double)g2_min / 4.0) > rho)) ++g2_min;
-    k_lsd_pre<<<d.n * 3, PT, smem, st>>>(d, g2_min, planesB, b.lsdw, b.pix, b.pixxy, b.used, b.pixcount, b.g2max, b.flags);
+    k_lsd_pre<<<d.n * 3, PT, smem, st>>>(d, g2_min, planesB, b.lsdw, b.pix, b.pixcount, b.g2max, b.flags);
     ++g_launches;
 }
 

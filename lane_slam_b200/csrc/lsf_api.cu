@@ -177,8 +177,7 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     b.dy = nullptr;
     CKC(dalloc(&b.lsdw, n * 3 * (size_t)ctx->sh * ctx->swp));
     CKC(dalloc(&b.pix, n * 3 * ctx->pixcap));
-    CKC(dalloc(&b.pixxy, n * 3 * ctx->pixcap));
-    CKC(dalloc(&b.used, n * 3 * ctx->pixcap));
+    CKC(dalloc(&b.nbr, n * 3 * ctx->pixcap * 8));
     CKC(dalloc(&b.order, n * 3 * ctx->pixcap));
     CKC(dalloc(&b.reg, n * 3 * ctx->pixcap * 2));
     CKC(dalloc(&b.pixcount, n * 3));
@@ -213,7 +212,7 @@ extern "C" void lsf_destroy(lsf_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     Buffers &b = ctx->b;
-    void *ptrs[] = {b.src, b.planesA, b.planesB, b.gray, b.dx, b.lsdw, b.pix, b.pixxy, b.used, b.order, b.reg, b.pixcount,
+    void *ptrs[] = {b.src, b.planesA, b.planesB, b.gray, b.dx, b.lsdw, b.pix, b.nbr, b.order, b.reg, b.pixcount,
                     b.g2max, b.rawseg, b.cand, b.candcount, b.candlist, b.candseg, b.candok, b.segcount, b.frame_off, b.flags, b.o_color, b.o_lines, b.o_normals, b.o_centers,
                     b.o_pixn, b.o_nf32, b.o_ground, b.o_keep, b.o_desc, b.o_frame, b.o_midx, b.o_mdist, ctx->map,
                     ctx->knn_scratch, ctx->tap_tmp, ctx->seg_in, ctx->carry};
