@@ -642,7 +642,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow(Dims d, const LsdWord *__restri
 // ---- kernel 2: NFA validation with LSD_REFINE_ADV rectangle improvement, one warp per candidate ---------------
 constexpr int VAL_WARPS = 4;
 
-__global__ void __launch_bounds__(VAL_WARPS * 32) k_lsd_validate(Dims d, const LsdWord *__restrict__ lsdw, const LsdPix *__restrict__ pix,
+__global__ void __launch_bounds__(VAL_WARPS * 32, 6) k_lsd_validate(Dims d, const LsdWord *__restrict__ lsdw, const LsdPix *__restrict__ pix,
                                                                 const int *__restrict__ pixcount, const LsdCand *__restrict__ cand,
                                                                 const uint2 *__restrict__ candlist, const int *__restrict__ flags,
                                                                 LsdSeg *__restrict__ candseg, u8 *__restrict__ candok)
@@ -718,7 +718,7 @@ void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st)
 
 void launch_lsd_validate(const Dims &d, Buffers &b, cudaStream_t st)
 {
-    k_lsd_validate<<<148 * 8, VAL_WARPS * 32, 0, st>>>(d, b.lsdw, b.pix, b.pixcount, b.cand, b.candlist, b.flags, b.candseg, b.candok);
+    k_lsd_validate<<<148 * 6, VAL_WARPS * 32, 0, st>>>(d, b.lsdw, b.pix, b.pixcount, b.cand, b.candlist, b.flags, b.candseg, b.candok);
     ++g_launches;
     k_lsd_emit<<<(d.n * 3 + 3) / 4, 128, 0, st>>>(d, b.candcount, b.candseg, b.candok, b.rawseg, b.segcount);
     ++g_launches;

@@ -254,7 +254,7 @@ static void make_tma(lsf_ctx *ctx, const u8 *src, int n, int sh, int sw, size_t 
     if (ctx->tma.valid && ctx->tma_src == src && ctx->tma_n == n && ctx->tma_h == sh && ctx->tma_w == sw && ctx->tma_pitch == pitch) return;
     ctx->tma.valid = 0;
     if (getenv("LSF_NO_TMA")) return;
-    if (sw < 128 || sh < 40 || (pitch % 16) != 0 || (((uintptr_t)src) % 16) != 0 || ((pitch * sh) % 16) != 0) return;
+    if (sw < 128 || sh < 40 || ((sw * 3) % 4) != 0 || (pitch % 16) != 0 || (((uintptr_t)src) % 16) != 0 || ((pitch * sh) % 16) != 0) return;
     static PFN_encodeTiled enc = nullptr;
     static bool tried = false;
     if (!tried) {
@@ -266,11 +266,12 @@ static void make_tma(lsf_ctx *ctx, const u8 *src, int n, int sh, int sw, size_t 
             enc = (PFN_encodeTiled)fn;
     }
     if (!enc) return;
-    cuuint64_t gdim[3] = {(cuuint64_t)sw * 3, (cuuint64_t)sh, (cuuint64_t)n};
+    // uint32 elements: the box may be 104 words (416 bytes) wide; 8-bit elements cap the box at 256 bytes
+    cuuint64_t gdim[3] = {(cuuint64_t)sw * 3 / 4, (cuuint64_t)sh, (cuuint64_t)n};
     cuuint64_t gstr[2] = {(cuuint64_t)pitch, (cuuint64_t)pitch * sh};
-    cuuint32_t box[3] = {224, 36, 1};
+    cuuint32_t box[3] = {104, 20, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&ctx->tma.map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)src, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(&ctx->tma.map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)src, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (g_debug_sync) fprintf(stderr, "[lsf] cuTensorMapEncodeTiled -> %d\n", (int)r);
     if (r != CUDA_SUCCESS) return;
