@@ -392,7 +392,7 @@ __device__ __forceinline__ double slope_d(double ax, double ay, double bx, doubl
     return (ceil(by) != ceil(ay)) ? (bx - ax) / (by - ay) : 0.0;
 }
 
-__device__ double rect_nfa(const Img &im, const Rect &r, bool verbose = false)
+__device__ __noinline__ double rect_nfa(const Img &im, const Rect &r)
 {
     const int lane = threadIdx.x & 31;
     double hw = r.width / 2.0, dyhw = r.dy * hw, dxhw = r.dx * hw;
@@ -422,7 +422,6 @@ __device__ double rect_nfa(const Img &im, const Rect &r, bool verbose = false)
             xa = max(to_int_x86(ceil(ll)), 0);
             int xb = min(to_int_x86(rl), im.W - 1);
             cnt = xb >= xa ? xb - xa + 1 : 0;
-            if (verbose) printf("   row %d ll=%.6f rl=%.6f xa=%d xb=%d\n", y, ll, rl, xa, xb);
         }
         // inclusive scan of the span lengths
         int incl = cnt;
@@ -450,50 +449,44 @@ __device__ double rect_nfa(const Img &im, const Rect &r, bool verbose = false)
         }
     }
     alg = __reduce_add_sync(FULL, alg);
-    if (verbose && lane == 0) printf("   tot=%d alg=%d ys=%d ye=%d\n", tot, alg, ys, ye);
     return nfa_d(tot, alg, r.p, im.logNT);
 }
 
+// LSD_REFINE_ADV rectangle improvement.  The reference's five trial phases (finer precision, narrower, one
+// side in, other side in, finer precision again) run as one loop around a single rect_nfa call site: the
+// NFA scan is large, and 21 inlined copies of it made the kernel instruction-cache bound (ncu: no_instruction).
 __device__ double rect_improve(const Img &im, Rect &rec)
 {
     const double log_eps = 0.0, delta = 0.5, delta_2 = 0.25;
-    double log_nfa = rect_nfa(im, rec);
-    if (log_nfa > log_eps) return log_nfa;
+    double log_nfa = 0;
     Rect r = rec;
-    for (int n = 0; n < 5; ++n) {
-        r.p /= 2; r.prec = r.p * kPI;
-        double v = rect_nfa(im, r);
-        if (v > log_nfa) { log_nfa = v; rec = r; }
-    }
-    if (log_nfa > log_eps) return log_nfa;
-    r = rec;
-    for (int n = 0; n < 5; ++n) {
-        if ((r.width - delta) >= 0.5) {
-            r.width -= delta;
-            double v = rect_nfa(im, r);
-            if (v > log_nfa) { log_nfa = v; rec = r; }
+    for (int step = 0; step <= 25; ++step) {
+        const int phase = step == 0 ? 0 : 1 + (step - 1) / 5;
+        if (step > 0 && (step - 1) % 5 == 0) {   // phase boundary: stop as soon as the rectangle is meaningful
+            if (log_nfa > log_eps) break;
+            r = rec;
         }
-    }
-    if (log_nfa > log_eps) return log_nfa;
-    for (int sgn = 1; sgn >= -1; sgn -= 2) {
-        r = rec;
-        for (int n = 0; n < 5; ++n) {
-            if ((r.width - delta) >= 0.5) {
-                r.x1 += sgn * -r.dy * delta_2; r.y1 += sgn * r.dx * delta_2;
-                r.x2 += sgn * -r.dy * delta_2; r.y2 += sgn * r.dx * delta_2;
-                r.width -= delta;
-                double v = rect_nfa(im, r);
-                if (v > log_nfa) { log_nfa = v; rec = r; }
+        bool eval = true;
+        if (phase == 1) {
+            r.p /= 2; r.prec = r.p * kPI;
+        } else if (phase >= 2) {
+            eval = (r.width - delta) >= 0.5;
+            if (eval) {
+                if (phase == 2) {
+                    r.width -= delta;
+                } else if (phase == 5) {
+                    r.p /= 2; r.prec = r.p * kPI;
+                } else {
+                    const double sgn = phase == 3 ? 1.0 : -1.0;
+                    r.x1 += sgn * -r.dy * delta_2; r.y1 += sgn * r.dx * delta_2;
+                    r.x2 += sgn * -r.dy * delta_2; r.y2 += sgn * r.dx * delta_2;
+                    r.width -= delta;
+                }
             }
         }
-        if (log_nfa > log_eps) return log_nfa;
-    }
-    r = rec;
-    for (int n = 0; n < 5; ++n) {
-        if ((r.width - delta) >= 0.5) {
-            r.p /= 2; r.prec = r.p * kPI;
+        if (eval) {
             double v = rect_nfa(im, r);
-            if (v > log_nfa) { log_nfa = v; rec = r; }
+            if (step == 0 || v > log_nfa) { log_nfa = v; rec = r; }
         }
     }
     return log_nfa;
