@@ -245,9 +245,15 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()
     l0 = fe.launch_count()
-    dt_dev, stage_ms, _, b = timed(dev, args.steps)
+    dt_dev, _, _, b = timed(dev, args.steps)
     launches = fe.launch_count() - l0
     dt_e2e, _, d2h_bytes, b = timed(pinned.numpy(), args.steps)
+    # per-kernel times for the roofline: same steps on ONE stream (chunk pipeline off) so that the library's
+    # CUDA events bracket each kernel; not part of `value` / `e2e`
+    fe.set_chunk_frames(-1)
+    step(dev)
+    _, stage_ms, _, _ = timed(dev, args.steps)
+    fe.set_chunk_frames(0)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([dt_dev, dt_e2e], dtype=torch.float64, device="cuda")
@@ -283,7 +289,7 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": 1e3 * dt_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": n, "img_size": [H, W], "top_cutoff": 0, "k": K_NN,
+        "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": n, "pipeline": "8 chunks x 4 streams, H2D of chunk c+1 overlaps kernels of chunk c", "img_size": [H, W], "top_cutoff": 0, "k": K_NN,
                    "l2": "inputs 921.6 MB per step exceed the 126 MB L2 (no flush needed)",
                    "segments_per_step": int(b.n_segments), "kept_per_step": int(b.keep.sum())},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(n * H * W * 3), "d2h_bytes_per_step": int(d2h_bytes),

@@ -68,7 +68,10 @@ typedef struct lsf_config {
     int32_t max_segments_per_color; /* per frame and colour */
     int32_t max_pixels_per_color;   /* LSD support pixels per frame and colour */
     int32_t device;              /* CUDA device ordinal */
-    int32_t reserved[7];
+    int32_t chunk_frames;        /* frames per pipeline chunk: a batch is cut into chunks whose host->device copy and
+                                    kernels overlap on several streams.  0 = automatic (about n/8, one chunk below 64
+                                    frames), < 0 = never chunk (one stream; lsf_last_timings then lists every kernel) */
+    int32_t reserved[6];
 } lsf_config;
 
 /*
@@ -131,6 +134,9 @@ LSF_API const char *lsf_last_error(const lsf_ctx *ctx); /* ctx may be NULL: last
 
 /* Replaces: LineDetectorNode.cbTransform (line_detector_node.py:112-114).  Takes effect next batch. */
 LSF_API int lsf_set_color_transform(lsf_ctx *ctx, const float scale[3], const float shift[3]);
+
+/* Change lsf_config.chunk_frames of a live ctx (same meaning); takes effect at the next batch. */
+LSF_API int lsf_set_chunk_frames(lsf_ctx *ctx, int chunk_frames);
 
 /* Replaces: LineDetectorNode.processImage_ (line_detector_node.py:141-213) for n frames at once,
  * i.e. cv2.resize/crop, AntiInstagram.applyTransform + convertScaleAbs, LineDetectorLSD.setImage and

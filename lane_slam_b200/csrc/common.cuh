@@ -34,20 +34,20 @@ struct Dims {
     int segcap;            // segment capacity per colour image
     int identity_geom;     // 1: no resize (dh==src_h, dw==src_w)
     int identity_color;    // 1: AntiInstagram scale==1, shift==0
-    int debug;             // LSF_TRACE_LSD: device printf of every LSD candidate
+    int debug;             // LSF_TRACE_LSD: bit 0 device printf of every LSD candidate, bit 1 grow cycle counters
+    int f0;                // first frame of this launch inside the batch (TMA coordinate; every other buffer is pre-offset)
+    int img0;              // = 3 * f0: first colour image of this launch (absolute ids in the candidate work list)
 };
 
 // one entry per 32 scaled pixels: defined-angle bits + number of defined pixels before this word
 struct LsdWord { u32 bits; u32 base; };
 
-// per LSD support pixel (raster order inside one colour image), 32 bytes
+// per LSD support pixel (raster order inside one colour image), 16 bytes.  The level-line angle in radians
+// is double(deg) * pi/180 exactly as the reference computes it from the float fastAtan2 result.
 struct __align__(16) LsdPix {
-    double ang;     // level-line angle in radians: double(fastAtan2 degrees) * pi/180
-    float c, s;     // cosf / sinf of float(ang)
+    float deg;      // fastAtan2 level-line angle in degrees
+    float c, s;     // cosf / sinf of float(angle in radians)
     u32 g2;         // gx^2 + gy^2 (norm = sqrt(g2/4))
-    u32 xy;         // (y << 16) | x in the scaled image
-    u32 used;       // region-growing USED flag
-    u32 pad;
 };
 constexpr u32 LSD_NONE = 0xffffffffu;
 
@@ -79,9 +79,12 @@ struct Buffers {
     short *dx, *dy;     // [n][h][w]  (descriptor path)
     LsdWord *lsdw;      // [n*3][sh][swp]
     LsdPix *pix;        // [n*3][pixcap]
-    u32 *nbr;           // [n*3][pixcap][8] compact indices of the 8 neighbours (row-major, centre skipped) or LSD_NONE
+    u32 *pxy;           // [n*3][pixcap]  (y << 16) | x in the scaled image
+    float2 *scs;        // [n*3][pixcap]  float(cos), float(sin) of the double angle (sums of a region seeded here)
+    u32 *fat;           // [n*3][pixcap][40] per pixel: index, angle, cos, sin, g2 of its 8 neighbours (LSD_NONE = undefined)
     u32 *order;         // [n*3][pixcap]  seed order (compact indices)
-    u32 *reg;           // [n*3][2*pixcap] region point list + scratch
+    uint4 *reg;         // [n*3][2*pixcap] region point list {idx, xy, g2, angle bits} + scratch
+    u32 *usedbits;      // [n*3][ceil(pixcap/32)] USED bitmap, only when it does not fit in shared memory
     int *pixcount;      // [n*3]
     u32 *g2max;         // [n*3]
     LsdCand *cand;      // [n*3][segcap]  candidates after refine, in seed order

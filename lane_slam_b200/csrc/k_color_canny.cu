@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(NT) k_color_canny(const __grid_constant__ CUte
         if (tid == 0) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(ROWB * BOX_Y)
                          : "memory");
-            int c0 = (tx0 * 3 - XOFF) / 4, c1 = ty0 - HALO + d.top, c2 = f;   // uint32 elements
+            int c0 = (tx0 * 3 - XOFF) / 4, c1 = ty0 - HALO + d.top, c2 = f + d.f0;   // uint32 elements
             asm volatile(
                 "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                 ::"r"(smem_u32(tile)), "l"(&tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar_a)

@@ -5,7 +5,7 @@
 // Replaces the first half of cv2.LineSegmentDetector.detect (line_detector_lsd.py:64-67):
 // GaussianBlur + resize + ll_angle.  Input is a packed bit-plane (edge_color is
 // 0/255), so the source costs N/8 bytes; the output is sparse: one {bits, base} word per 32 scaled
-// pixels plus one 16-byte record per support pixel (0.3-3 % of the pixels).
+// pixels plus one 16-byte record (+ 4-byte position) per support pixel (0.3-3 % of the pixels).
 //
 // One CTA per (frame, colour) walks the image in bands of 8 scaled rows, so the running count of support
 // pixels (= raster-order compact index) is known without a second pass.  Edges are sparse: per band the
@@ -46,7 +46,7 @@ __device__ __forceinline__ int warp_compact(const u8 *flag, int n, u16 *list)
 }
 
 __global__ void __launch_bounds__(PT) k_lsd_pre(Dims d, u32 g2_min, const u32 *__restrict__ planesB, LsdWord *__restrict__ lsdw,
-                                               LsdPix *__restrict__ pix,
+                                               LsdPix *__restrict__ pix, u32 *__restrict__ pxy,
                                                int *__restrict__ pixcount, u32 *__restrict__ g2max, int *__restrict__ flags)
 {
     extern __shared__ __align__(16) u8 smraw[];
@@ -73,9 +73,9 @@ __global__ void __launch_bounds__(PT) k_lsd_pre(Dims d, u32 g2_min, const u32 *_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     LsdWord *ow = lsdw + (size_t)img * sh * swp;
     LsdPix *opix = pix + (size_t)img * d.pixcap;
+    u32 *opxy = pxy + (size_t)img * d.pixcap;
     if (tid == 0) { s_run = 0; s_gmax = 0; }
     u32 my_gmax = 0;
-    const int wlast = (w - 1) >> 5;   // source word holding the last image column
     __syncthreads();
 
     for (int ys0 = 0; ys0 < sh; ys0 += BR) {
@@ -235,14 +235,12 @@ __global__ void __launch_bounds__(PT) k_lsd_pre(Dims d, u32 g2_min, const u32 *_
                     double ar = (double)a * (3.14159265358979323846 / 180.0);
                     float af = (float)ar;
                     LsdPix p;
-                    p.ang = ar;
+                    p.deg = a;
                     p.c = (float)cos((double)af);   // cosf(float(angle)), correctly rounded
                     p.s = (float)sin((double)af);
                     p.g2 = g2;
-                    p.xy = ((u32)ys << 16) | (u32)xs;
-                    p.used = 0;
-                    p.pad = 0;
                     opix[idx] = p;
+                    opxy[idx] = ((u32)ys << 16) | (u32)xs;
                 }
             }
         }
@@ -277,7 +275,7 @@ void launch_lsd_pre(const Dims &d, const u32 *planesB, Buffers &b, cudaStream_t 
     const double rho = 2.0 / sin(3.14159265358979323846 * 22.5 / 180.0);
     u32 g2_min = 0;
     while (!(sqrt((double)g2_min / 4.0) > rho)) ++g2_min;
-    k_lsd_pre<<<d.n * 3, PT, smem, st>>>(d, g2_min, planesB, b.lsdw, b.pix, b.pixcount, b.g2max, b.flags);
+    k_lsd_pre<<<d.n * 3, PT, smem, st>>>(d, g2_min, planesB, b.lsdw, b.pix, b.pxy, b.pixcount, b.g2max, b.flags);
     ++g_launches;
 }
 

@@ -45,6 +45,11 @@ struct lsf_ctx {
     // TMA
     TmaDesc tma;
     const u8 *tma_src; int tma_n, tma_h, tma_w; size_t tma_pitch;
+    // chunk pipeline: copy stream, compute streams, per-chunk events
+    cudaStream_t copy_st;
+    cudaStream_t aux[4];
+    std::vector<cudaEvent_t> ev_copy, ev_done;
+    cudaEvent_t ev_begin;
     // timing
     std::vector<StageTime> events;
     int n_events;
@@ -133,6 +138,9 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     ctx->seg_in = nullptr; ctx->seg_in_cap = 0;
     ctx->tma.valid = 0; ctx->tma_src = nullptr;
     ctx->n_events = 0;
+    ctx->copy_st = nullptr; ctx->ev_begin = nullptr;
+    for (int i = 0; i < 4; ++i) ctx->aux[i] = nullptr;
+    ctx->carry = nullptr; ctx->carry_n = 0; ctx->carry_cap = 0; ctx->h_small = nullptr; ctx->st = nullptr;
     memset(&ctx->b, 0, sizeof(ctx->b));
     auto bail = [&](int code, const std::string &msg) { g_create_error = msg; lsf_destroy(ctx); return code; };
 #define CKC(call)                                                                                  \
@@ -142,6 +150,9 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     } while (0)
     CKC(cudaSetDevice(ctx->device));
     CKC(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) CKC(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&ctx->ev_begin, cudaEventDisableTiming));
     ctx->max_batch = cfg->max_batch > 0 ? cfg->max_batch : 1;
     ctx->max_src_h = cfg->max_src_h > 0 ? cfg->max_src_h : cfg->img_h;
     ctx->max_src_w = cfg->max_src_w > 0 ? cfg->max_src_w : cfg->img_w;
@@ -177,7 +188,10 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     b.dy = nullptr;
     CKC(dalloc(&b.lsdw, n * 3 * (size_t)ctx->sh * ctx->swp));
     CKC(dalloc(&b.pix, n * 3 * ctx->pixcap));
-    CKC(dalloc(&b.nbr, n * 3 * ctx->pixcap * 8));
+    CKC(dalloc(&b.pxy, n * 3 * ctx->pixcap));
+    CKC(dalloc(&b.fat, n * 3 * ctx->pixcap * 40));
+    CKC(dalloc(&b.scs, n * 3 * ctx->pixcap));
+    CKC(dalloc(&b.usedbits, n * 3 * (size_t)((ctx->pixcap + 31) / 32)));
     CKC(dalloc(&b.order, n * 3 * ctx->pixcap));
     CKC(dalloc(&b.reg, n * 3 * ctx->pixcap * 2));
     CKC(dalloc(&b.pixcount, n * 3));
@@ -212,13 +226,18 @@ extern "C" void lsf_destroy(lsf_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     Buffers &b = ctx->b;
-    void *ptrs[] = {b.src, b.planesA, b.planesB, b.gray, b.dx, b.lsdw, b.pix, b.nbr, b.order, b.reg, b.pixcount,
+    void *ptrs[] = {b.src, b.planesA, b.planesB, b.gray, b.dx, b.lsdw, b.pix, b.pxy, b.fat, b.scs, b.usedbits, b.order, b.reg, b.pixcount,
                     b.g2max, b.rawseg, b.cand, b.candcount, b.candlist, b.candseg, b.candok, b.segcount, b.frame_off, b.flags, b.o_color, b.o_lines, b.o_normals, b.o_centers,
                     b.o_pixn, b.o_nf32, b.o_ground, b.o_keep, b.o_desc, b.o_frame, b.o_midx, b.o_mdist, ctx->map,
                     ctx->knn_scratch, ctx->tap_tmp, ctx->seg_in, ctx->carry};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
     for (auto &e : ctx->events) cudaEventDestroy(e.ev);
+    for (auto &e : ctx->ev_copy) cudaEventDestroy(e);
+    for (auto &e : ctx->ev_done) cudaEventDestroy(e);
+    if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+    if (ctx->copy_st) cudaStreamDestroy(ctx->copy_st);
+    for (int i = 0; i < 4; ++i) if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
     if (ctx->st) cudaStreamDestroy(ctx->st);
     delete ctx;
 }
@@ -229,6 +248,13 @@ extern "C" int lsf_set_color_transform(lsf_ctx *ctx, const float scale[3], const
 {
     if (!ctx || !scale || !shift) return LSF_E_ARG;
     for (int i = 0; i < 3; ++i) { ctx->cfg.ai_scale[i] = scale[i]; ctx->cfg.ai_shift[i] = shift[i]; }
+    return LSF_OK;
+}
+
+extern "C" int lsf_set_chunk_frames(lsf_ctx *ctx, int chunk_frames)
+{
+    if (!ctx) return LSF_E_ARG;
+    ctx->cfg.chunk_frames = chunk_frames;
     return LSF_OK;
 }
 
@@ -358,36 +384,90 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
     d.identity_color = 1;
     for (int i = 0; i < 3; ++i) if (ctx->cp.ai_scale[i] != 1.f || ctx->cp.ai_shift[i] != 0.f) d.identity_color = 0;
 
+    d.f0 = 0; d.img0 = 0;
     ctx->n_events = 0;
     mark(ctx, "start");
+    int chunk = ctx->cfg.chunk_frames;
+    if (getenv("LSF_CHUNK_FRAMES")) chunk = atoi(getenv("LSF_CHUNK_FRAMES"));
+    if (chunk == 0) chunk = n >= 64 ? std::max(32, (n + 7) / 8) : n;
+    if (chunk < 0 || chunk > n || (d.debug & 2)) chunk = n;
+    const int nchunks = (n + chunk - 1) / chunk;
+    const bool host_in = mem_kind != LSF_MEM_DEVICE;
     const u8 *src;
-    if (mem_kind == LSF_MEM_DEVICE) {
+    if (!host_in) {
         src = bgr; d.src_pitch = pitch; d.src_frame = pitch * src_h;
     } else {
         d.src_pitch = (size_t)src_w * 3; d.src_frame = d.src_pitch * src_h;
-        CK(cudaMemcpy2DAsync(b.src, d.src_pitch, bgr, pitch, (size_t)src_w * 3, (size_t)src_h * n, cudaMemcpyHostToDevice, ctx->st));
         src = b.src;
-        mark(ctx, "h2d");
     }
     ctx->last_src = src; ctx->d = d; ctx->have_batch = true;
     if (d.identity_geom) make_tma(ctx, src, n, src_h, src_w, d.src_pitch); else ctx->tma.valid = 0;
-
     CK(cudaMemsetAsync(b.flags, 0, 4 * sizeof(int), ctx->st));
-    launch_color_canny(d, ctx->cp, src, ctx->tma, b.planesA, b.gray, ctx->st);
-    mark(ctx, "color_canny");
-    launch_hysteresis(d, ctx->cfg.dilation_kernel_size, b.planesA, b.planesB, ctx->st);
-    mark(ctx, "hysteresis_dilate");
-    launch_lsd_pre(d, b.planesB, b, ctx->st);
-    mark(ctx, "lsd_pre");
-    launch_lsd_core(d, b, ctx->st);
-    mark(ctx, "lsd_grow");
+    if (nchunks == 1) {
+        if (host_in) {
+            CK(cudaMemcpy2DAsync(b.src, d.src_pitch, bgr, pitch, (size_t)src_w * 3, (size_t)src_h * n, cudaMemcpyHostToDevice, ctx->st));
+            mark(ctx, "h2d");
+        }
+        launch_color_canny(d, ctx->cp, src, ctx->tma, b.planesA, b.gray, ctx->st);
+        mark(ctx, "color_canny");
+        launch_hysteresis(d, ctx->cfg.dilation_kernel_size, b.planesA, b.planesB, ctx->st);
+        mark(ctx, "hysteresis_dilate");
+        launch_lsd_pre(d, b.planesB, b, ctx->st);
+        mark(ctx, "lsd_pre");
+        launch_lsd_core(d, b, ctx->st);
+        mark(ctx, "lsd_grow");
+        if (stages & LSF_STAGE_DESCRIBE) {
+            launch_gray_sobel(d, b.gray, b.dx, nullptr, ctx->st);
+            mark(ctx, "gray_sobel");
+        }
+    } else {
+        // Chunk pipeline: chunk c is copied on the copy stream while earlier chunks compute on the aux streams
+        // (round robin).  The region-growing kernel is a long chain of dependent steps that leaves the SMs
+        // mostly idle, so it overlaps with the dense kernels of the following chunks.
+        while ((int)ctx->ev_copy.size() < nchunks) {
+            cudaEvent_t e0, e1;
+            CK(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+            ctx->ev_copy.push_back(e0); ctx->ev_done.push_back(e1);
+        }
+        CK(cudaEventRecord(ctx->ev_begin, ctx->st));     // after the flags reset (and everything of the previous call)
+        CK(cudaStreamWaitEvent(ctx->copy_st, ctx->ev_begin, 0));
+        for (int i = 0; i < 4; ++i) CK(cudaStreamWaitEvent(ctx->aux[i], ctx->ev_begin, 0));
+        const size_t ps = (size_t)d.h * d.wp, N = (size_t)d.h * d.w;
+        for (int c = 0; c < nchunks; ++c) {
+            const int f0 = c * chunk, nc = std::min(chunk, n - f0);
+            cudaStream_t cs = ctx->aux[c & 3];
+            if (host_in) {
+                CK(cudaMemcpy2DAsync(b.src + (size_t)f0 * d.src_frame, d.src_pitch, bgr + (size_t)f0 * pitch * src_h, pitch,
+                                     (size_t)src_w * 3, (size_t)src_h * nc, cudaMemcpyHostToDevice, ctx->copy_st));
+                CK(cudaEventRecord(ctx->ev_copy[c], ctx->copy_st));
+                CK(cudaStreamWaitEvent(cs, ctx->ev_copy[c], 0));
+            }
+            Dims dc = d;
+            dc.n = nc; dc.f0 = f0; dc.img0 = 3 * f0;
+            Buffers bc = b;
+            const size_t i0 = (size_t)3 * f0;
+            bc.planesA += (size_t)f0 * PA_COUNT * ps; bc.planesB += (size_t)f0 * PB_COUNT * ps;
+            bc.gray += (size_t)f0 * N; bc.dx += (size_t)f0 * N * 2;
+            bc.lsdw += i0 * d.sh * d.swp; bc.pix += i0 * d.pixcap; bc.pxy += i0 * d.pixcap; bc.scs += i0 * d.pixcap;
+            bc.fat += i0 * d.pixcap * 40; bc.order += i0 * d.pixcap; bc.reg += i0 * 2 * d.pixcap;
+            bc.usedbits += i0 * (size_t)((d.pixcap + 31) / 32);
+            bc.pixcount += i0; bc.g2max += i0; bc.cand += i0 * d.segcap; bc.candcount += i0;
+            launch_color_canny(dc, ctx->cp, src + (size_t)f0 * d.src_frame, ctx->tma, bc.planesA, bc.gray, cs);
+            launch_hysteresis(dc, ctx->cfg.dilation_kernel_size, bc.planesA, bc.planesB, cs);
+            launch_lsd_pre(dc, bc.planesB, bc, cs);
+            launch_lsd_core(dc, bc, cs);
+            if (stages & LSF_STAGE_DESCRIBE) launch_gray_sobel(dc, bc.gray, bc.dx, nullptr, cs);
+            CK(cudaEventRecord(ctx->ev_done[c], cs));
+            CK(cudaStreamWaitEvent(ctx->st, ctx->ev_done[c], 0));
+        }
+        mark(ctx, "chunks(h2d+color_canny+hysteresis+lsd_pre+lsd_grow+gray_sobel)");
+    }
     launch_lsd_validate(d, b, ctx->st);
     mark(ctx, "lsd_validate");
     launch_segments(d, ctx->cam, b, (stages & LSF_STAGE_GROUND) ? 1 : 0, ctx->st);
     mark(ctx, "segments");
     if (stages & LSF_STAGE_DESCRIBE) {
-        launch_gray_sobel(d, b.gray, b.dx, nullptr, ctx->st);
-        mark(ctx, "gray_sobel");
         launch_lbd(d, b.o_lines, b.o_frame, b.outcap, b.frame_off + n, b.dx, nullptr, b.o_desc, ctx->st);
         mark(ctx, "lbd");
     }

@@ -86,7 +86,8 @@ class FrontEnd:
 
     def __init__(self, configuration=None, img_size=(120, 160), top_cutoff=40, camera=None, homography=None,
                  src_size=(480, 640), max_batch=1, device=0, ai_scale=(1, 1, 1), ai_shift=(0, 0, 0),
-                 max_segments_per_color=0, max_pixels_per_color=0, max_segments_per_frame=1024, pinned=False):
+                 max_segments_per_color=0, max_pixels_per_color=0, max_segments_per_frame=1024, pinned=False,
+                 chunk_frames=0):
         self._lib = _lib.load()
         conf = check_detector_configuration(configuration if configuration is not None
                                             else DEFAULT_DETECTOR_CONFIGURATION)
@@ -121,6 +122,7 @@ class FrontEnd:
         cfg.max_segments_per_color = int(max_segments_per_color)
         cfg.max_pixels_per_color = int(max_pixels_per_color)
         cfg.device = int(device)
+        cfg.chunk_frames = int(chunk_frames)   # 0 auto, < 0 one stream (per-kernel timings), > 0 frames per pipeline chunk
         self.cfg = cfg
         self.img_size, self.top_cutoff, self.max_batch = tuple(img_size), int(top_cutoff), int(max_batch)
         self._ctx = C.c_void_p()
@@ -213,6 +215,10 @@ class FrontEnd:
         """AntiInstagramTransform update (line_detector_node.py:112-114); takes effect at the next batch."""
         sc = (C.c_float * 3)(*[float(x) for x in scale]); sf = (C.c_float * 3)(*[float(x) for x in shift])
         self._check(self._lib.lsf_set_color_transform(self._ctx, sc, sf))
+
+    def set_chunk_frames(self, chunk_frames):
+        """Pipeline chunking of the next batches: 0 automatic, < 0 one stream (timings() then lists every kernel)."""
+        self._check(self._lib.lsf_set_chunk_frames(self._ctx, int(chunk_frames)))
 
     def project_filter(self, pixels_normalized, color):
         """ground_projection + line_sanity over S segments -> (ground f64 [S,4], keep bool [S])."""
