@@ -39,7 +39,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", OUT]
+    extra = ["-DLSF_GROW_PROF"] if os.environ.get("LSF_GROW_PROF") else []   # developer aid: cycle counters in k_lsd_grow
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", OUT]
     subprocess.check_call(cmd)
     return OUT
 

@@ -83,6 +83,12 @@ struct Buffers {
     float2 *scs;        // [n*3][pixcap]  float(cos), float(sin) of the double angle (sums of a region seeded here)
     u32 *fat;           // [n*3][pixcap][40] per pixel: index, angle, cos, sin, g2 of its 8 neighbours (LSD_NONE = undefined)
     u32 *order;         // [n*3][pixcap]  seed order (compact indices)
+    u32 *label, *csize, *coff;   // [n*3][pixcap] connected components: root label, size (at roots), seed-list cursor (at roots)
+    u32 *corder, *cpos; // [n*3][pixcap]  seed order partitioned by component; position of each entry in order[]
+    uint2 *tasks;       // [n*3][256]     {offset into corder, size} of every component with >= min_reg pixels
+    uint2 *worklist;    // [n*3*256]      (image, task) work list of the growing kernel: big tasks from the front, small from the back
+    int *taskctr;       // [64][4]        per pipeline chunk: big tasks, small tasks, work cursor
+    u32 *candrank;      // [n*3][segcap]  position of the candidate's seed in order[] (restores the acceptance order)
     uint4 *reg;         // [n*3][2*pixcap] region point list {idx, xy, g2, angle bits} + scratch
     u32 *usedbits;      // [n*3][ceil(pixcap/32)] USED bitmap, only when it does not fit in shared memory
     int *pixcount;      // [n*3]

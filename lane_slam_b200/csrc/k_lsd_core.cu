@@ -179,7 +179,11 @@ __device__ double nfa_d(int n, int k, double p, double logNT)
 // ---- region growing -----------------------------------------------------------------------------------
 // LSF_GROW_PROF=1 (env) -> d.debug & 2: per-image cycle / event counters of k_lsd_grow, printed by the host
 struct Prof { long long t_total, t_grow, t_wait, t_rect, t_refine; int grows, rounds, accepts, refresh, cands; };
-#define GPROF(stmt) do { stmt; } while (0)
+#ifdef LSF_GROW_PROF
+#define GPROF(...) __VA_ARGS__
+#else
+#define GPROF(...)
+#endif
 constexpr int FAT_WORDS = 40;   // [idx x8][angle(deg) x8][cos x8][sin x8][g2 x8], neighbours row-major, centre skipped
 constexpr int RING = 16;        // queue entries whose fat record can be resident at once
 constexpr float kDEG2RADf = (float)kDEG2RAD, k3_2PIf = (float)k3_2PI, k2PIf = (float)k2PI;
@@ -190,8 +194,7 @@ struct GrowSm {
     __align__(16) u32 ring[RING][FAT_WORDS];      // fat records of queue positions q (slot q % RING)
     __align__(16) u32 seedrec[32][FAT_WORDS];     // fat records of the current batch of 32 seed candidates
     u32 qxy[RING];                                // xy of the queue entries in the ring
-    u32 acc_idx[32];                              // pixels accepted by the current commit, in order
-    float acc_c[32], acc_s[32];
+    float2 acc_cs[32];                            // cos / sin of the pixels accepted by the current commit, in order
     Seq3 seq;
 };
 
@@ -218,23 +221,27 @@ __device__ __forceinline__ void commit(const Img &im, GrowSm &sm, u32 acc, int i
 {
     const int lane = threadIdx.x & 31;
     const int cnt = __popc(acc), rank = __popc(acc & ((1u << lane) - 1u));
-    const int room = pf == nreg ? max(0, min(cnt, i + RING - nreg)) : 0;   // positions that get a ring slot now
+    const int room = pf == nreg ? min(cnt, i + RING - nreg) : 0;   // positions that get a ring slot now (may be <= 0)
     __syncwarp();
     if ((acc >> lane) & 1u) {
         set_used<SB>(im, (u32)idx);
         im.reg[nreg + rank] = make_uint4((u32)idx, xy, g2, __float_as_uint(deg));
-        sm.acc_idx[rank] = (u32)idx; sm.acc_c[rank] = c; sm.acc_s[rank] = s;
-        if (rank < room) sm.qxy[(nreg + rank) % RING] = xy;
+        sm.acc_cs[rank] = make_float2(c, s);
+        if (rank < room) {
+            const u32 slot = (u32)(nreg + rank) & (RING - 1);
+            sm.qxy[slot] = xy;
+            const u32 *src = im.fat + (size_t)idx * FAT_WORDS;
+            u32 *dst = sm.ring[slot];
+#pragma unroll
+            for (int t = 0; t < FAT_WORDS / 4; ++t) cp_async16(dst + t * 4, src + t * 4);
+        }
     }
     __syncwarp();
-    for (int t = lane; t < room * (FAT_WORDS / 4); t += 32) {
-        const int r = t / (FAT_WORDS / 4), part = t - r * (FAT_WORDS / 4);
-        cp_async16(&sm.ring[(nreg + r) % RING][part * 4], im.fat + (size_t)sm.acc_idx[r] * FAT_WORDS + part * 4);
-    }
-    pf += room;
+    if (room > 0) pf += room;
     for (int r = 0; r < cnt; ++r) {
-        sumdx = __fadd_rn(sumdx, sm.acc_c[r]);
-        sumdy = __fadd_rn(sumdy, sm.acc_s[r]);
+        const float2 cs = sm.acc_cs[r];
+        sumdx = __fadd_rn(sumdx, cs.x);
+        sumdy = __fadd_rn(sumdy, cs.y);
     }
     nreg += cnt;
 }
@@ -243,15 +250,18 @@ template <bool SB>
 __device__ int grow(const Img &im, GrowSm &sm, Prof &pr, int seed, float seed_deg, u32 seed_g2, u32 seed_xy, float seed_c, float seed_s,
                     const u32 *seed_rec, double prec, double &reg_angle_out)
 {
-    const long long t_in = clock64();
-    GPROF(++pr.grows);
+    GPROF(const long long t_in = clock64(); ++pr.grows);
     const int lane = threadIdx.x & 31;
     const u32 lt = (1u << lane) - 1u;
     const int g = lane >> 3, j = lane & 7;
     const int jj = j < 4 ? j : j + 1;                       // 3x3 position of neighbour j
-    const int ndx = jj % 3 - 1, ndy = jj / 3 - 1;
+    const int nd = ((jj / 3 - 1) << 16) + (jj % 3 - 1);     // xy offset of neighbour j
     const bool lazy = prec <= 0.6;
     const float precf = (float)prec;
+    // drift per accepted pixel: it was aligned with the angle of its time, so it sits within prec + Bmax of the
+    // checkpoint; its component perpendicular to S0 is at most sin(prec + Bmax), the parallel one is positive
+    constexpr float Bmax = 0.2f;
+    const float kfac = lazy ? 1.01f * sinf(precf + Bmax) : 0.f;
     int nreg = 1;
     double reg_angle = (double)seed_deg * kDEG2RAD;         // exact region angle whenever m == 0
     float sumdx = seed_c, sumdy = seed_s;                   // (float)cos(reg_angle), (float)sin(reg_angle)
@@ -260,22 +270,28 @@ __device__ int grow(const Img &im, GrowSm &sm, Prof &pr, int seed, float seed_de
         set_used<SB>(im, (u32)seed);
         sm.qxy[0] = seed_xy;
     }
-    if (!seed_rec && lane < FAT_WORDS / 4) cp_async16(&sm.ring[0][lane * 4], im.fat + (size_t)seed * FAT_WORDS + lane * 4);
+    if (seed_rec) {
+        cp_async_wait_all();
+        __syncwarp();
+        if (lane < FAT_WORDS / 4) reinterpret_cast<uint4 *>(sm.ring[0])[lane] = reinterpret_cast<const uint4 *>(seed_rec)[lane];
+    } else if (lane < FAT_WORDS / 4) {
+        cp_async16(&sm.ring[0][lane * 4], im.fat + (size_t)seed * FAT_WORDS + lane * 4);
+    }
     int pf = 1;                        // queue positions < pf have their record in flight / resident
     float th0f = (float)reg_angle;     // checkpoint angle (float copy) ...
-    int m = 0, mmax = 0;               // ... pixels accepted since then, and how many the drift bound tolerates
-    float kB = 1.21f;                  // B(m) = m * kB + slack;  kB = 1.21 / |S0|  (asin(x) <= 1.11 x for x <= 0.69)
+    int m = 0;                         // ... pixels accepted since then
+    float kB = kfac;                   // B(m) = m * kB + slack, kB = sin(prec + Bmax) / |S0|; |S0| = 1 at the seed
     for (int i = 0; i < nreg;) {
         const int navail = min(4, nreg - i);
         // (rare) queue entries beyond the ring at acceptance time: fetch them now
         while (pf < nreg && pf < i + RING) {
             uint4 e = im.reg[pf];
-            if (lane < FAT_WORDS / 4) cp_async16(&sm.ring[pf % RING][lane * 4], im.fat + (size_t)e.x * FAT_WORDS + lane * 4);
-            if (lane == 0) sm.qxy[pf % RING] = e.y;
+            if (lane < FAT_WORDS / 4) cp_async16(&sm.ring[pf & (RING - 1)][lane * 4], im.fat + (size_t)e.x * FAT_WORDS + lane * 4);
+            if (lane == 0) sm.qxy[pf & (RING - 1)] = e.y;
             ++pf;
         }
         {
-            const long long tw = clock64();
+            GPROF(const long long tw = clock64());
             cp_async_wait_all();
             __syncwarp();
             GPROF(pr.t_wait += clock64() - tw; ++pr.rounds);
@@ -284,68 +300,65 @@ __device__ int grow(const Img &im, GrowSm &sm, Prof &pr, int seed, float seed_de
         float deg = 0.f, c = 0.f, s = 0.f;
         u32 g2 = 0, xy = 0;
         if (g < navail) {
-            const int pos = i + g;
-            const u32 *rec = (pos == 0 && seed_rec) ? seed_rec : sm.ring[pos % RING];
+            const u32 slot = (u32)(i + g) & (RING - 1);
+            const u32 *rec = sm.ring[slot];
             u32 ni = rec[j];
             if (ni != LSD_NONE && !is_used<SB>(im, ni)) {
                 idx = (int)ni;
                 deg = __uint_as_float(rec[8 + j]); c = __uint_as_float(rec[16 + j]); s = __uint_as_float(rec[24 + j]);
                 g2 = rec[32 + j];
-                u32 cxy = sm.qxy[pos % RING];
-                xy = (u32)((int)cxy + (ndy << 16) + ndx);
+                xy = sm.qxy[slot] + (u32)nd;
             }
         }
         u32 R = __ballot_sync(FULL, idx >= 0);          // undecided visits
         if (!R) { i += navail; continue; }
         const u32 peers = __match_any_sync(FULL, idx);  // visits of the same pixel (from several queue entries)
-        u32 done = 0;                                   // visits accepted in this round
         const float angf = deg * kDEG2RADf;
         float d0f = fabsf(th0f - angf);
         if (d0f > k3_2PIf) d0f = fabsf(d0f - k2PIf);
         while (R) {
             // ---- bulk step: decide every visit that is clear of the tolerance band ----
-            const bool in = (R >> lane) & 1u;
-            const int mub = m + __popc(R & lt);
-            const float B = (float)mub * kB + 0.002f;
-            const bool okb = in && lazy && mub <= mmax;
-            const u32 ma = __ballot_sync(FULL, okb && d0f <= precf - B);
-            const u32 mn = __ballot_sync(FULL, okb && d0f >= precf + B);
-            const u32 unsure = R & ~(ma | mn);
-            const u32 below = unsure ? ((1u << (__ffs(unsure) - 1)) - 1u) : FULL;
-            u32 acc = ma & below;
-            if (acc) {
-                acc = __ballot_sync(FULL, ((acc >> lane) & 1u) && (peers & acc & lt) == 0);   // first visit of a pixel wins
-                commit<SB>(im, sm, acc, idx, xy, g2, deg, c, s, i, nreg, pf, sumdx, sumdy);
-                m += __popc(acc);
-                done |= acc;
-                GPROF(pr.accepts += __popc(acc));
+            if (lazy) {
+                const bool in = (R >> lane) & 1u;
+                // pass 1: loose bound (every pending visit before this one may be accepted) -> certainly rejected visits
+                float B = (float)(m + __popc(R & lt)) * kB + 0.002f;
+                const u32 mn1 = __ballot_sync(FULL, in && B <= Bmax && d0f >= precf + B);
+                // pass 2: those cannot add to the drift
+                B = (float)(m + __popc(R & ~mn1 & lt)) * kB + 0.002f;
+                const bool okb = in && B <= Bmax;
+                const u32 ma = __ballot_sync(FULL, okb && d0f <= precf - B);
+                const u32 mn = __ballot_sync(FULL, okb && d0f >= precf + B) | mn1;
+                const u32 unsure = R & ~(ma | mn);
+                const u32 below = unsure ? ((unsure & (0u - unsure)) - 1u) : FULL;   // visits before the first unsure one
+                u32 acc = ma & below;
+                R &= ~below;
+                if (acc) {
+                    acc = __ballot_sync(FULL, ((acc >> lane) & 1u) && (peers & acc & lt) == 0);   // first visit of a pixel wins
+                    commit<SB>(im, sm, acc, idx, xy, g2, deg, c, s, i, nreg, pf, sumdx, sumdy);
+                    m += __popc(acc);
+                    GPROF(pr.accepts += __popc(acc));
+                    R &= ~__ballot_sync(FULL, (peers & acc) != 0);   // later visits of pixels accepted just now: USED
+                }
+                if (!R) break;
             }
-            R &= ~below;
-            R &= ~__ballot_sync(FULL, (peers & done) != 0);   // later visits of pixels accepted just now: USED
-            if (!(R & unsure)) continue;                      // the unsure visit was such a duplicate (or none was)
             // ---- exact step: the reference's test at the current angle, up to the first accepted visit ----
             if (m > 0) {
                 reg_angle = (double)fast_atan2_deg(sumdy, sumdx) * kDEG2RAD;
                 th0f = (float)reg_angle; m = 0;
-                const float S0 = sqrtf(sumdx * sumdx + sumdy * sumdy);
-                kB = 1.21f / S0; mmax = (int)(0.69f * S0);
+                kB = kfac * rsqrtf(sumdx * sumdx + sumdy * sumdy);
                 d0f = fabsf(th0f - angf);
                 if (d0f > k3_2PIf) d0f = fabsf(d0f - k2PIf);
                 GPROF(++pr.refresh);
+                if (lazy) continue;      // most visits are decidable from the new checkpoint
             }
             const u32 al = __ballot_sync(FULL, idx >= 0 && aligned_ang((double)deg * kDEG2RAD, reg_angle, prec)) & R;
             if (!al) break;                                   // nothing else in this round is aligned
-            const int k = __ffs(al) - 1;
-            commit<SB>(im, sm, 1u << k, idx, xy, g2, deg, c, s, i, nreg, pf, sumdx, sumdy);
+            const u32 kbit = al & (0u - al);
+            commit<SB>(im, sm, kbit, idx, xy, g2, deg, c, s, i, nreg, pf, sumdx, sumdy);
             m = 1;
-            done |= 1u << k;
             GPROF(++pr.accepts);
-            R &= ~((2u << k) - 1u);
-            R &= ~__ballot_sync(FULL, (peers & done) != 0);
-            if (!lazy) {   // wide tolerance (refine's tau): keep the angle exact after every pixel
-                reg_angle = (double)fast_atan2_deg(sumdy, sumdx) * kDEG2RAD;
-                th0f = (float)reg_angle; m = 0;
-            }
+            R &= ~(kbit | (kbit - 1u));
+            R &= ~__ballot_sync(FULL, (peers & kbit) != 0);
         }
         __syncwarp();  // used bits / qxy of this round are visible to the next one
         i += navail;
@@ -671,180 +684,364 @@ __device__ __forceinline__ void setup_img(Img &im, const Dims &d, int img, const
     im.logNT = 5.0 * (log10((double)im.W) + log10((double)im.H)) / 2.0 + log10(11.0);
 }
 
-// ---- kernel 0: seed order + fat neighbour records (fully parallel, one CTA per image) ---------------------------
-// warp 0: stable counting sort of the support pixels by bin = int(norm * 1023 / max_norm), descending (raster
-//         order inside a bin) -> order[];  warps 1..7: one fat record per support pixel, 8 lanes per pixel.
-__global__ void __launch_bounds__(256) k_lsd_index(Dims d, const LsdWord *__restrict__ lsdw, const LsdPix *__restrict__ pix,
-                                                  const u32 *__restrict__ pxy, const int *__restrict__ pixcount,
-                                                  const u32 *__restrict__ g2max, u32 *__restrict__ fat, u32 *__restrict__ order,
-                                                  float2 *__restrict__ scs)
+// ---- kernel 0: seed order, fat neighbour records, connected components (fully parallel, one CTA per image) -------
+// Region growing never leaves an 8-connected component of the support pixels, USED flags included, so the search
+// of an image splits exactly into independent searches per component (seeds visited in the image's seed order
+// restricted to the component; candidates merged back by the seed's position in the image order).  Components
+// smaller than min_reg cannot produce a candidate and are dropped here.
+//   phase 1  warp 0: stable counting sort of the support pixels by bin = int(norm * 1023 / max_norm), descending
+//            (raster order inside a bin) -> order[];  warps 1..7: fat record of every pixel (8 lanes per pixel),
+//            union-find merge with the W / NW / N / NE neighbours, seed cos/sin
+//   phase 2  flatten labels (root = smallest index of the component), component sizes
+//   phase 3  block scan over the roots: component slot, offset of its seed list; tasks appended to the work list
+//            (components of >= BIG_COMP pixels from the front, the others from the back: long chains start first)
+//   phase 4  warp 0: stable partition of order[] by component -> corder[] (+ cpos[] = position in order[])
+constexpr int MAXC = 256;        // components (tasks) per image; an image with more is searched as one task
+constexpr int BIG_COMP = 768;
+constexpr int SL_MAX = 8192;     // support pixels whose union-find labels fit in shared memory
+
+// labels only ever decrease and always point into the same component (path halving included)
+__device__ __forceinline__ u32 uf_find(u32 *label, u32 x)
 {
-    __shared__ u32 hist[1024];
-    const int img = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Img im;
-    setup_img(im, d, img, lsdw, pix, pxy, nullptr, nullptr, pixcount);
-    const int n = im.n;
-    if (n == 0) return;
-    if (warp == 0) {
-        u32 *ord = order + (size_t)img * d.pixcap;
-        const double max_grad = sqrt((double)g2max[img] / 4.0);
-        const double bin_coef = max_grad > 0 ? 1023.0 / max_grad : 0.0;
-        for (int i = lane; i < 1024; i += 32) hist[i] = 0;
-        __syncwarp();
-        for (int i = lane; i < n; i += 32) {
-            int bin = (int)(sqrt((double)im.pix[i].g2 / 4.0) * bin_coef);
-            atomicAdd(&hist[1023 - bin], 1u);
-        }
-        __syncwarp();
-        {
-            // exclusive scan of 1024 counters: lane owns 32 consecutive entries
-            u32 loc = 0;
-            for (int q = 0; q < 32; ++q) loc += hist[lane * 32 + q];
-            u32 incl = loc;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                u32 v = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += v;
-            }
-            u32 run = incl - loc;
-            for (int q = 0; q < 32; ++q) { u32 c = hist[lane * 32 + q]; hist[lane * 32 + q] = run; run += c; }
-        }
-        __syncwarp();
-        for (int i0 = 0; i0 < n; i0 += 32) {
-            int i = i0 + lane;
-            bool valid = i < n;
-            u32 key = valid ? (u32)(1023 - (int)(sqrt((double)im.pix[i].g2 / 4.0) * bin_coef)) : (2048u + (u32)lane);
-            u32 mm = __match_any_sync(FULL, key);
-            int leader = __ffs(mm) - 1;
-            u32 off = 0;
-            if (valid && lane == leader) { off = hist[key]; hist[key] = off + __popc(mm); }
-            off = __shfl_sync(FULL, off, leader);
-            if (valid) ord[off + __popc(mm & ((1u << lane) - 1u))] = (u32)i;
-            __syncwarp();
-        }
-    } else {
-        const int j = lane & 7, jj = j < 4 ? j : j + 1;
-        const int ndx = jj % 3 - 1, ndy = jj / 3 - 1;
-        // what a region starts its sums with when this pixel is the seed: float(cos(angle)), float(sin(angle)) of the
-        // DOUBLE angle (the per-pixel c/s are cosf/sinf of the float angle)
-        float2 *ocs = scs + (size_t)img * d.pixcap;
-        for (int p = threadIdx.x - 32; p < n; p += 224) {
-            const double a = (double)im.pix[p].deg * kDEG2RAD;
-            ocs[p] = make_float2((float)cos(a), (float)sin(a));
-        }
-        u32 *out = fat + (size_t)img * d.pixcap * FAT_WORDS;
-        for (int p = (warp - 1) * 4 + (lane >> 3); p < n; p += 28) {
-            u32 xy = im.pxy[p];
-            int xx = (int)(xy & 0xffffu) + ndx, yy = (int)(xy >> 16) + ndy, r = -1;
-            if (xx >= 0 && xx < im.W && yy >= 0 && yy < im.H) r = lookup(im, xx, yy);
-            uint4 t = make_uint4(0, 0, 0, 0);
-            if (r >= 0) t = *reinterpret_cast<const uint4 *>(&im.pix[r]);
-            u32 *rec = out + (size_t)p * FAT_WORDS + j;
-            rec[0] = r >= 0 ? (u32)r : LSD_NONE;
-            rec[8] = t.x; rec[16] = t.y; rec[24] = t.z; rec[32] = t.w;
-        }
+    volatile u32 *vl = label;
+    u32 p = vl[x];
+    while (p != x) {
+        u32 gp = vl[p];
+        if (gp != p) atomicMin(&label[x], gp);
+        x = p; p = gp;
+    }
+    return x;
+}
+__device__ __forceinline__ void uf_union(u32 *label, u32 a, u32 b)
+{
+    while (true) {
+        a = uf_find(label, a); b = uf_find(label, b);
+        if (a == b) return;
+        if (a < b) { u32 t = a; a = b; b = t; }
+        u32 old = atomicMin(&label[a], b);     // root a (the larger index) goes under b
+        if (old == a) return;
+        a = old;                                // a was re-parented meanwhile: merge its new parent with b
     }
 }
 
+// stable counting-sort scatter of one warp's contiguous segment [lo, hi) of a sequence: key(pos) in [0, nkeys),
+// cursor[key] = first output slot for this warp's elements with that key (shared memory, private to the warp).
+// KEY(pos, valid&) and EMIT(pos, dst) are lambdas; elements with valid == false are skipped.
+template <typename KeyFn, typename EmitFn>
+__device__ __forceinline__ void warp_stable_scatter(int lo, int hi, u32 *cursor, KeyFn key_of, EmitFn emit)
+{
+    const int lane = threadIdx.x & 31;
+    for (int p0 = lo; p0 < hi; p0 += 32) {
+        const int pos = p0 + lane;
+        bool ok = pos < hi;
+        u32 key = 0;
+        if (ok) key = key_of(pos, ok);
+        const u32 mk = ok ? key : (0x80000000u + (u32)lane);
+        const u32 mm = __match_any_sync(FULL, mk);
+        const int leader = __ffs(mm) - 1;
+        u32 base = 0;
+        if (ok && lane == leader) { base = cursor[key]; cursor[key] = base + __popc(mm); }
+        base = __shfl_sync(FULL, base, leader);
+        if (ok) emit(pos, base + __popc(mm & ((1u << lane) - 1u)));
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_lsd_index(Dims d, const LsdWord *__restrict__ lsdw, const LsdPix *__restrict__ pix,
+                                                  const u32 *__restrict__ pxy, const int *__restrict__ pixcount,
+                                                  const u32 *__restrict__ g2max, u32 *__restrict__ fat, u32 *__restrict__ order,
+                                                  float2 *__restrict__ scs, u32 *__restrict__ label_, u32 *__restrict__ csize_,
+                                                  u32 *__restrict__ coff_, u32 *__restrict__ corder_, u32 *__restrict__ cpos_,
+                                                  uint2 *__restrict__ tasks, uint2 *__restrict__ worklist, int worklist_cap,
+                                                  int *__restrict__ taskctr, int *__restrict__ candcount)
+{
+    // 32 KB used twice: union-find forest of the image (phases 1-2, when it fits; else the global label array),
+    // then per-warp key counts / cursors of the two stable partitions (bins, then component slots)
+    __shared__ u32 sbuf[8 * 1024];
+    u32 (*cnt)[1024] = reinterpret_cast<u32 (*)[1024]>(sbuf);
+    u32 *s_label = sbuf;
+    __shared__ u32 s_wsum[8];
+    __shared__ u32 s_ncomp, s_off;
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    Img im;
+    setup_img(im, d, img, lsdw, pix, pxy, nullptr, nullptr, pixcount);
+    const int n = im.n;
+    if (tid == 0) candcount[img] = 0;
+    if (n == 0) return;
+    const size_t ibase = (size_t)img * d.pixcap;
+    u32 *label = label_ + ibase, *csize = csize_ + ibase, *coff = coff_ + ibase, *corder = corder_ + ibase, *cpos = cpos_ + ibase;
+    u32 *ord = order + ibase;
+    const int min_reg = (int)(-im.logNT / log10(22.5 / 180.0));
+    const double max_grad = sqrt((double)g2max[img] / 4.0);
+    const double bin_coef = max_grad > 0 ? 1023.0 / max_grad : 0.0;
+    // every warp owns a contiguous segment (multiple of 32) of any n-long sequence
+    const int seg = (((n + 7) / 8) + 31) & ~31;
+    const int p_lo = min(n, warp * seg), p_hi = min(n, p_lo + seg);
+    u32 *lab = n <= SL_MAX ? s_label : label;
+    for (int i = tid; i < n; i += 256) { lab[i] = (u32)i; csize[i] = 0; }
+    if (tid == 0) { s_ncomp = 0; s_off = 0; }
+    __syncthreads();
+    // ---- phase 1: fat records + unions; seed cos/sin ----
+    for (int i = p_lo + lane; i < p_hi; i += 32) {
+        const LsdPix t = im.pix[i];
+        // what a region starts its sums with when this pixel is the seed: float(cos(angle)), float(sin(angle)) of the
+        // DOUBLE angle (the per-pixel c/s are cosf/sinf of the float angle)
+        const double a = (double)t.deg * kDEG2RAD;
+        scs[ibase + i] = make_float2((float)cos(a), (float)sin(a));
+    }
+    {
+        const int j = lane & 7, jj = j < 4 ? j : j + 1;
+        const int ndx = jj % 3 - 1, ndy = jj / 3 - 1;
+        u32 *out = fat + ibase * FAT_WORDS;
+        constexpr int U = 4;      // pixels per thread in flight (three dependent loads each)
+        for (int p0 = 0; p0 < n; p0 += 32 * U) {
+            int pp[U], r[U];
+            u32 xy[U];
+            uint4 t[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) { pp[u] = p0 + 32 * u + (tid >> 3); xy[u] = pp[u] < n ? im.pxy[pp[u]] : 0u; }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                r[u] = -1;
+                if (pp[u] < n) {
+                    int xx = (int)(xy[u] & 0xffffu) + ndx, yy = (int)(xy[u] >> 16) + ndy;
+                    if (xx >= 0 && xx < im.W && yy >= 0 && yy < im.H) r[u] = lookup(im, xx, yy);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                t[u] = make_uint4(0, 0, 0, 0);
+                if (r[u] >= 0) t[u] = *reinterpret_cast<const uint4 *>(&im.pix[r[u]]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (pp[u] < n) {
+                    u32 *rec = out + (size_t)pp[u] * FAT_WORDS + j;
+                    rec[0] = r[u] >= 0 ? (u32)r[u] : LSD_NONE;
+                    rec[8] = t[u].x; rec[16] = t[u].y; rec[24] = t[u].z; rec[32] = t[u].w;
+                }
+            }
+            // merge with the already visited neighbours.  NW-N, N-NE and W-NW are neighbours of each other (merged at
+            // their own turn), so one merge with N is enough when N exists, at most two otherwise.
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int rNW = __shfl_sync(FULL, r[u], 0, 8), rN = __shfl_sync(FULL, r[u], 1, 8),
+                          rNE = __shfl_sync(FULL, r[u], 2, 8), rW = __shfl_sync(FULL, r[u], 3, 8);
+                if (j == 0 && pp[u] < n) {
+                    const u32 p = (u32)pp[u];
+                    if (rN >= 0) uf_union(lab, p, (u32)rN);
+                    else {
+                        if (rNE >= 0) uf_union(lab, p, (u32)rNE);
+                        if (rNW >= 0) uf_union(lab, p, (u32)rNW);
+                        else if (rW >= 0) uf_union(lab, p, (u32)rW);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: flatten labels, component sizes; then bin counts of the warp's pixels and their cursors ----
+    for (int i = tid; i < n; i += 256) {
+        u32 r = uf_find(lab, (u32)i);
+        label[i] = r;
+        atomicAdd(&csize[r], 1u);
+    }
+    __syncthreads();
+    for (int i = tid; i < 8 * 1024; i += 256) sbuf[i] = 0;
+    __syncthreads();
+    for (int i = p_lo + lane; i < p_hi; i += 32) {
+        int bin = (int)(sqrt((double)im.pix[i].g2 / 4.0) * bin_coef);
+        atomicAdd(&cnt[warp][1023 - bin], 1u);
+    }
+    __syncthreads();
+    {
+        // exclusive scan over (key, warp); thread owns keys 4*tid .. 4*tid+3
+        u32 sum = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            for (int w = 0; w < 8; ++w) sum += cnt[w][4 * tid + q];
+        u32 incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        u32 run = incl - sum;
+        for (int k = 0; k < warp; ++k) run += s_wsum[k];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            for (int w = 0; w < 8; ++w) { u32 c = cnt[w][4 * tid + q]; cnt[w][4 * tid + q] = run; run += c; }
+    }
+    __syncthreads();
+    // ---- phase 3: seed order (stable scatter of the warp's pixels); component slots, tasks ----
+    warp_stable_scatter(p_lo, p_hi, cnt[warp],
+                        [&](int pos, bool &) { return (u32)(1023 - (int)(sqrt((double)im.pix[pos].g2 / 4.0) * bin_coef)); },
+                        [&](int pos, u32 dst) { ord[dst] = (u32)pos; });
+    uint2 *tk = tasks + (size_t)img * MAXC;
+    for (int i = tid; i < n; i += 256) {
+        if (label[i] == (u32)i) {
+            const u32 sz = csize[i];
+            if (sz >= (u32)min_reg) {
+                const u32 slot = atomicAdd(&s_ncomp, 1u);   // slots in any order: tasks are independent of each other
+                coff[i] = slot;
+                if (slot < MAXC) tk[slot] = make_uint2(atomicAdd(&s_off, sz), sz);
+            }
+        }
+    }
+    __syncthreads();
+    const u32 ncomp = s_ncomp;
+    const bool one_task = ncomp > MAXC;          // too many components: search the image as a whole
+    if (one_task && tid == 0) tk[0] = make_uint2(0u, (u32)n);
+    const u32 ntask = one_task ? 1u : ncomp;
+    for (int i = tid; i < 8 * MAXC; i += 256) cnt[i / MAXC][i % MAXC] = 0;
+    __syncthreads();
+    if (tid < ntask) {
+        const bool big = tk[tid].y >= (u32)BIG_COMP;
+        const int slot = big ? atomicAdd(&taskctr[0], 1) : worklist_cap - 1 - atomicAdd(&taskctr[1], 1);
+        worklist[slot] = make_uint2((u32)img, (u32)tid);
+    }
+    // ---- phase 4: seed list of every component, in image seed order (stable partition of order[]) ----
+    if (one_task) {
+        for (int i = tid; i < n; i += 256) { corder[i] = ord[i]; cpos[i] = (u32)i; }
+        return;
+    }
+    // label[i] <- component slot of pixel i (LSD_NONE for the dropped small components)
+    for (int i = tid; i < n; i += 256) {
+        const u32 r = label[i];
+        label[i] = csize[r] >= (u32)min_reg ? coff[r] : LSD_NONE;
+    }
+    __syncthreads();
+    for (int pos = p_lo + lane; pos < p_hi; pos += 32) {
+        const u32 sl = label[ord[pos]];
+        if (sl != LSD_NONE) atomicAdd(&cnt[warp][sl], 1u);
+    }
+    __syncthreads();
+    if (tid < (int)ncomp) {
+        u32 run = tk[tid].x;
+        for (int w = 0; w < 8; ++w) { const u32 c = cnt[w][tid]; cnt[w][tid] = run; run += c; }
+    }
+    __syncthreads();
+    warp_stable_scatter(p_lo, p_hi, cnt[warp],
+                        [&](int pos, bool &ok) { const u32 sl = label[ord[pos]]; ok = sl != LSD_NONE; return sl; },
+                        [&](int pos, u32 dst) { corder[dst] = ord[pos]; cpos[dst] = (u32)pos; });
+}
+
 // ---- kernel 1: seeds, region growing, rectangle fit, density refinement -> candidate rectangles ----------
-// One warp per (frame, colour) image; strictly sequential in the reference's seed order because growing and
-// refining change which pixels later seeds may use.  NFA validation does not touch that state, so it is
-// deferred to kernel 2, where every candidate gets its own warp.  Blocks are ordered colour-major (all white
-// images first): white images hold the most support pixels and must not start last.
+// Persistent single-warp blocks pull (image, component) tasks from the work list.  Inside a task everything is
+// strictly sequential in the reference's seed order, because growing and refining change which pixels later
+// seeds may use.  NFA validation does not touch that state, so it is deferred to kernel 2, where every
+// candidate gets its own warp.
 template <bool SB>
 __global__ void __launch_bounds__(32) k_lsd_grow(Dims d, const LsdWord *__restrict__ lsdw, const LsdPix *__restrict__ pix,
                                                 const u32 *__restrict__ pxy, const float2 *__restrict__ scs, const u32 *__restrict__ fat,
-                                                const u32 *__restrict__ order, uint4 *__restrict__ reg,
+                                                const u32 *__restrict__ corder_, const u32 *__restrict__ cpos_,
+                                                const uint2 *__restrict__ tasks, const uint2 *__restrict__ worklist, int worklist_cap,
+                                                int *__restrict__ taskctr, uint4 *__restrict__ reg,
                                                 const int *__restrict__ pixcount, u32 *__restrict__ used_global,
-                                                int used_words, LsdCand *__restrict__ cand, int *__restrict__ candcount,
-                                                uint2 *__restrict__ candlist, int *__restrict__ flags, long long *__restrict__ prof)
+                                                int used_words, LsdCand *__restrict__ cand, u32 *__restrict__ candrank,
+                                                int *__restrict__ candcount, uint2 *__restrict__ candlist, int *__restrict__ flags,
+                                                long long *__restrict__ prof)
 {
     extern __shared__ __align__(16) u8 smraw[];
-    Prof pr = {};
-    const long long t_start = clock64();
     GrowSm &sm = *reinterpret_cast<GrowSm *>(smraw);
     const int lane = threadIdx.x;
-    const int img = (blockIdx.x % d.n) * 3 + blockIdx.x / d.n;
-    Img im;
-    setup_img(im, d, img, lsdw, pix, pxy, fat, reg, pixcount);
-    im.used = SB ? reinterpret_cast<u32 *>(smraw + sizeof(GrowSm)) : used_global + (size_t)img * used_words;
-    const float2 *seedcs = scs + (size_t)img * d.pixcap;
-    const u32 *ord = order + (size_t)img * d.pixcap;
-    const int n = im.n;
-    if (n == 0) {
-        if (lane == 0) candcount[img] = 0;
-        return;
-    }
-    for (int i = lane; i < (n + 31) / 32; i += 32) im.used[i] = 0;
-    __syncwarp();
-
     const double prec = kPI * 22.5 / 180.0, p = 22.5 / 180.0;
-    const int min_reg = (int)(-im.logNT / log10(p));
-    int ncand = 0;
-    LsdCand *out = cand + (size_t)img * d.segcap;
-    int ci_next = lane < n ? (int)ord[lane] : -1;
-    for (int o0 = 0; o0 < n; o0 += 32) {
-        const int ci = ci_next;
-        ci_next = o0 + 32 + lane < n ? (int)ord[o0 + 32 + lane] : -1;
-        // this batch of 32 seed candidates: thin record, position, and (for the still unused ones) the fat record
-        uint4 tp = make_uint4(0, 0, 0, 0);
-        u32 cxy = 0;
-        float2 ccs = make_float2(0.f, 0.f);
-        bool want = ci >= 0 && !is_used<SB>(im, (u32)ci);
-        if (want) {
-            tp = *reinterpret_cast<const uint4 *>(&im.pix[ci]);
-            cxy = im.pxy[ci];
-            ccs = seedcs[ci];
-            const u32 *src = im.fat + (size_t)ci * FAT_WORDS;
+    while (true) {
+        Prof pr = {};
+        const long long t_start = clock64();
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&taskctr[2], 1);
+        t = __shfl_sync(FULL, t, 0);
+        const int nbig = taskctr[0], nsmall = taskctr[1];
+        if (t >= nbig + nsmall) break;
+        const uint2 wl = worklist[t < nbig ? t : worklist_cap - 1 - (t - nbig)];
+        const int img = (int)wl.x;
+        const uint2 tk = tasks[(size_t)img * MAXC + wl.y];
+        const int off = (int)tk.x, n = (int)tk.y;
+        Img im;
+        setup_img(im, d, img, lsdw, pix, pxy, fat, reg, pixcount);
+        im.reg += off;                    // region list of this component (scratch half = +pixcap stays inside the image's buffer)
+        im.used = SB ? reinterpret_cast<u32 *>(smraw + sizeof(GrowSm)) : used_global + (size_t)img * used_words;
+        const float2 *seedcs = scs + (size_t)img * d.pixcap;
+        const u32 *ord = corder_ + (size_t)img * d.pixcap + off;
+        const u32 *opos = cpos_ + (size_t)img * d.pixcap + off;
+        __syncwarp();
+        for (int i = lane; i < (im.n + 31) / 32; i += 32) im.used[i] = 0;
+        __syncwarp();
+        const int min_reg = (int)(-im.logNT / log10(p));
+        LsdCand *out = cand + (size_t)img * d.segcap;
+        u32 *orank = candrank + (size_t)img * d.segcap;
+        int ci_next = lane < n ? (int)ord[lane] : -1;
+        u32 pos_next = lane < n ? opos[lane] : 0u;
+        for (int o0 = 0; o0 < n; o0 += 32) {
+            const int ci = ci_next;
+            const u32 cpos = pos_next;
+            ci_next = o0 + 32 + lane < n ? (int)ord[o0 + 32 + lane] : -1;
+            pos_next = o0 + 32 + lane < n ? opos[o0 + 32 + lane] : 0u;
+            // this batch of 32 seed candidates: thin record, position, and (for the still unused ones) the fat record
+            uint4 tp = make_uint4(0, 0, 0, 0);
+            u32 cxy = 0;
+            float2 ccs = make_float2(0.f, 0.f);
+            bool want = ci >= 0 && !is_used<SB>(im, (u32)ci);
+            if (want) {
+                tp = *reinterpret_cast<const uint4 *>(&im.pix[ci]);
+                cxy = im.pxy[ci];
+                ccs = seedcs[ci];
+                const u32 *src = im.fat + (size_t)ci * FAT_WORDS;
 #pragma unroll
-            for (int t = 0; t < FAT_WORDS / 4; ++t) cp_async16(&sm.seedrec[lane][t * 4], src + t * 4);
-        }
-        const u32 pfmask = __ballot_sync(FULL, want);
-        int k = -1;
-        while (true) {
-            // seeds of this batch not yet visited and still unused *now*
-            __syncwarp();
-            u32 cnd = __ballot_sync(FULL, ci >= 0 && lane > k && !is_used<SB>(im, (u32)ci));
-            if (!cnd) break;
-            k = __ffs(cnd) - 1;
-            const int seed = __shfl_sync(FULL, ci, k);
-            const bool have = (pfmask >> k) & 1u;   // a seed released by an earlier refine was not pre-fetched
-            u32 sdeg = __shfl_sync(FULL, tp.x, k), sg2 = __shfl_sync(FULL, tp.w, k), sxy = __shfl_sync(FULL, cxy, k);
-            float sc = __shfl_sync(FULL, ccs.x, k), ss = __shfl_sync(FULL, ccs.y, k);
-            if (!have) {
-                sdeg = __float_as_uint(im.pix[seed].deg); sg2 = im.pix[seed].g2; sxy = im.pxy[seed];
-                float2 t = seedcs[seed];
-                sc = t.x; ss = t.y;
+                for (int q = 0; q < FAT_WORDS / 4; ++q) cp_async16(&sm.seedrec[lane][q * 4], src + q * 4);
             }
-            const u32 *srec = have ? sm.seedrec[k] : nullptr;
-            double reg_angle;
-            int nreg = grow<SB>(im, sm, pr, seed, __uint_as_float(sdeg), sg2, sxy, sc, ss, srec, prec, reg_angle);
-            if (nreg < min_reg) continue;
-            Rect rec;
-            long long t0 = clock64();
-            region2rect(im, sm.seq, nreg, reg_angle, prec, p, rec);
-            long long t1 = clock64();
-            bool okr = refine<SB>(im, sm, pr, nreg, reg_angle, prec, p, rec, sc, ss, srec);
-            GPROF(pr.t_rect += t1 - t0; pr.t_refine += clock64() - t1; ++pr.cands);
-            if (!okr) continue;
-            if (ncand < d.segcap && lane == 0) {
-                LsdCand c;
-                c.x1 = rec.x1; c.y1 = rec.y1; c.x2 = rec.x2; c.y2 = rec.y2;
-                c.width = rec.width; c.theta = rec.theta; c.dx = rec.dx; c.dy = rec.dy;
-                out[ncand] = c;
-                int slot = atomicAdd(&flags[3], 1);
-                candlist[slot] = make_uint2((u32)(img + d.img0), (u32)ncand);
+            const u32 pfmask = __ballot_sync(FULL, want);
+            int k = -1;
+            while (true) {
+                // seeds of this batch not yet visited and still unused *now*
+                __syncwarp();
+                u32 cnd = __ballot_sync(FULL, ci >= 0 && lane > k && !is_used<SB>(im, (u32)ci));
+                if (!cnd) break;
+                k = __ffs(cnd) - 1;
+                const int seed = __shfl_sync(FULL, ci, k);
+                const bool have = (pfmask >> k) & 1u;   // a seed released by an earlier refine was not pre-fetched
+                u32 sdeg = __shfl_sync(FULL, tp.x, k), sg2 = __shfl_sync(FULL, tp.w, k), sxy = __shfl_sync(FULL, cxy, k);
+                float sc = __shfl_sync(FULL, ccs.x, k), ss = __shfl_sync(FULL, ccs.y, k);
+                const u32 srank = __shfl_sync(FULL, cpos, k);   // position of the seed in the image's seed order
+                if (!have) {
+                    sdeg = __float_as_uint(im.pix[seed].deg); sg2 = im.pix[seed].g2; sxy = im.pxy[seed];
+                    float2 t2 = seedcs[seed];
+                    sc = t2.x; ss = t2.y;
+                }
+                const u32 *srec = have ? sm.seedrec[k] : nullptr;
+                double reg_angle;
+                int nreg = grow<SB>(im, sm, pr, seed, __uint_as_float(sdeg), sg2, sxy, sc, ss, srec, prec, reg_angle);
+                if (nreg < min_reg) continue;
+                Rect rec;
+                GPROF(long long t0 = clock64());
+                region2rect(im, sm.seq, nreg, reg_angle, prec, p, rec);
+                GPROF(long long t1 = clock64());
+                bool okr = refine<SB>(im, sm, pr, nreg, reg_angle, prec, p, rec, sc, ss, srec);
+                GPROF(pr.t_rect += t1 - t0; pr.t_refine += clock64() - t1; ++pr.cands);
+                if (!okr) continue;
+                if (lane == 0) {
+                    const int slot = atomicAdd(&candcount[img], 1);
+                    if (slot < d.segcap) {
+                        LsdCand c;
+                        c.x1 = rec.x1; c.y1 = rec.y1; c.x2 = rec.x2; c.y2 = rec.y2;
+                        c.width = rec.width; c.theta = rec.theta; c.dx = rec.dx; c.dy = rec.dy;
+                        out[slot] = c;
+                        orank[slot] = srank;
+                        const int gs = atomicAdd(&flags[3], 1);
+                        candlist[gs] = make_uint2((u32)(img + d.img0), (u32)slot);
+                    } else {
+                        atomicMax(&flags[1], slot + 1);
+                    }
+                }
             }
-            ++ncand;
         }
-    }
-    if (lane == 0) {
-        if (ncand > d.segcap) { atomicMax(&flags[1], ncand); ncand = d.segcap; }
-        candcount[img] = ncand;
-        if (prof) {
-            long long *o = prof + (size_t)img * 12;
+        if (lane == 0 && prof) {
+            long long *o = prof + (size_t)t * 12;
             o[0] = clock64() - t_start; o[1] = pr.t_grow; o[2] = pr.t_wait; o[3] = pr.t_rect; o[4] = pr.t_refine;
-            o[5] = pr.grows; o[6] = pr.rounds; o[7] = pr.accepts; o[8] = pr.refresh; o[9] = pr.cands; o[10] = n; o[11] = ncand;
+            o[5] = pr.grows; o[6] = pr.rounds; o[7] = pr.accepts; o[8] = pr.refresh; o[9] = pr.cands; o[10] = n; o[11] = img;
         }
     }
 }
@@ -885,24 +1082,30 @@ __global__ void __launch_bounds__(VAL_WARPS * 32, 6) k_lsd_validate(Dims d, cons
     }
 }
 
-// ---- kernel 3: keep the validated candidates, in candidate (= acceptance) order ------------------------------------
+// ---- kernel 3: keep the validated candidates, ordered by the position of their seed in the image's seed order
+// (= the reference's acceptance order; the component tasks of an image finish in arbitrary order) ---------------
 __global__ void __launch_bounds__(128) k_lsd_emit(Dims d, const int *__restrict__ candcount, const LsdSeg *__restrict__ candseg,
-                                                 const u8 *__restrict__ candok, LsdSeg *__restrict__ rawseg, int *__restrict__ segcount)
+                                                 const u8 *__restrict__ candok, const u32 *__restrict__ candrank,
+                                                 LsdSeg *__restrict__ rawseg, int *__restrict__ segcount)
 {
-    const int lane = threadIdx.x & 31;
-    const int img = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (img >= d.n * 3) return;
-    const int nc = candcount[img];
+    const int img = blockIdx.x, tid = threadIdx.x;
+    const int nc = min(candcount[img], d.segcap);
     const size_t base = (size_t)img * d.segcap;
-    int nout = 0;
-    for (int i0 = 0; i0 < nc; i0 += 32) {
-        int i = i0 + lane;
-        bool ok = i < nc && candok[base + i];
-        u32 m = __ballot_sync(FULL, ok);
-        if (ok) rawseg[base + nout + __popc(m & ((1u << lane) - 1u))] = candseg[base + i];
-        nout += __popc(m);
+    __shared__ int s_cnt;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int i = tid; i < nc; i += 128) {
+        if (!candok[base + i]) continue;
+        const u32 r = candrank[base + i];
+        int pos = 0;
+        for (int q = 0; q < nc; ++q) pos += (candok[base + q] && candrank[base + q] < r) ? 1 : 0;
+        rawseg[base + pos] = candseg[base + i];
+        ++mine;
     }
-    if (lane == 0) segcount[img] = nout;
+    if (mine) atomicAdd(&s_cnt, mine);
+    __syncthreads();
+    if (tid == 0) segcount[img] = s_cnt;
 }
 
 void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st)
@@ -919,7 +1122,9 @@ void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st)
         cudaMemcpyToSymbol(g_lgtab, &d_lgtab, sizeof(d_lgtab));
         tab_ready = true;
     }
-    k_lsd_index<<<d.n * 3, 256, 0, st>>>(d, b.lsdw, b.pix, b.pxy, b.pixcount, b.g2max, b.fat, b.order, b.scs);
+    const int nimg = d.n * 3, wl_cap = nimg * MAXC;
+    k_lsd_index<<<nimg, 256, 0, st>>>(d, b.lsdw, b.pix, b.pxy, b.pixcount, b.g2max, b.fat, b.order, b.scs, b.label, b.csize, b.coff,
+                                      b.corder, b.cpos, b.tasks, b.worklist, wl_cap, b.taskctr, b.candcount);
     ++g_launches;
     // USED bitmap: shared memory when it fits (the normal case), the global fallback buffer otherwise
     const int used_words = (d.pixcap + 31) / 32;
@@ -931,29 +1136,35 @@ void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st)
         cudaFuncSetAttribute(k_lsd_grow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = smem;
     }
+    const int grid = 148 * 20;     // persistent single-warp blocks (register-limited to about 20 per SM)
     long long *prof = nullptr;
-    if (d.debug & 2) cudaMalloc((void **)&prof, (size_t)d.n * 3 * 12 * sizeof(long long));
+    if (d.debug & 2) { cudaMalloc((void **)&prof, (size_t)wl_cap * 12 * sizeof(long long)); cudaMemsetAsync(prof, 0, (size_t)wl_cap * 12 * sizeof(long long), st); }
     if (used_global)
-        k_lsd_grow<false><<<d.n * 3, 32, smem, st>>>(d, b.lsdw, b.pix, b.pxy, b.scs, b.fat, b.order, b.reg, b.pixcount, used_global,
-                                                     used_words, b.cand, b.candcount, b.candlist, b.flags, prof);
+        k_lsd_grow<false><<<grid, 32, smem, st>>>(d, b.lsdw, b.pix, b.pxy, b.scs, b.fat, b.corder, b.cpos, b.tasks, b.worklist, wl_cap,
+                                                  b.taskctr, b.reg, b.pixcount, used_global, used_words, b.cand, b.candrank, b.candcount,
+                                                  b.candlist, b.flags, prof);
     else
-        k_lsd_grow<true><<<d.n * 3, 32, smem, st>>>(d, b.lsdw, b.pix, b.pxy, b.scs, b.fat, b.order, b.reg, b.pixcount, used_global,
-                                                    used_words, b.cand, b.candcount, b.candlist, b.flags, prof);
+        k_lsd_grow<true><<<grid, 32, smem, st>>>(d, b.lsdw, b.pix, b.pxy, b.scs, b.fat, b.corder, b.cpos, b.tasks, b.worklist, wl_cap,
+                                                 b.taskctr, b.reg, b.pixcount, used_global, used_words, b.cand, b.candrank, b.candcount,
+                                                 b.candlist, b.flags, prof);
     ++g_launches;
     if (prof) {
         // developer aid (LSF_TRACE_LSD=2): where the slowest image and the average image spend their cycles
-        std::vector<long long> h((size_t)d.n * 3 * 12);
+        std::vector<long long> h((size_t)wl_cap * 12);
         cudaStreamSynchronize(st);
         cudaMemcpy(h.data(), prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
         cudaFree(prof);
-        int worst = 0;
+        int worst = 0, nt = 0;
         double avg[12] = {0};
-        for (int i = 0; i < d.n * 3; ++i) {
+        for (int i = 0; i < wl_cap; ++i) {
+            if (h[(size_t)i * 12] == 0) continue;
+            ++nt;
             if (h[(size_t)i * 12] > h[(size_t)worst * 12]) worst = i;
-            for (int q = 0; q < 12; ++q) avg[q] += (double)h[(size_t)i * 12 + q] / (d.n * 3);
+            for (int q = 0; q < 12; ++q) avg[q] += (double)h[(size_t)i * 12 + q];
         }
-        const char *nm[12] = {"total", "grow", "wait", "rect", "refine", "grows", "rounds", "accepts", "refresh", "cands", "npix", "ncand"};
-        fprintf(stderr, "[lsf grow prof] worst image %d:", worst);
+        for (int q = 0; q < 12; ++q) avg[q] /= nt ? nt : 1;
+        const char *nm[12] = {"total", "grow", "wait", "rect", "refine", "grows", "rounds", "accepts", "refresh", "cands", "npix", "img"};
+        fprintf(stderr, "[lsf grow prof] %d tasks; worst task %d:", nt, worst);
         for (int q = 0; q < 12; ++q) fprintf(stderr, " %s=%lld", nm[q], h[(size_t)worst * 12 + q]);
         fprintf(stderr, "\n[lsf grow prof] mean:");
         for (int q = 0; q < 12; ++q) fprintf(stderr, " %s=%.0f", nm[q], avg[q]);
@@ -965,7 +1176,7 @@ void launch_lsd_validate(const Dims &d, Buffers &b, cudaStream_t st)
 {
     k_lsd_validate<<<148 * 6, VAL_WARPS * 32, 0, st>>>(d, b.lsdw, b.pix, b.pixcount, b.cand, b.candlist, b.flags, b.candseg, b.candok);
     ++g_launches;
-    k_lsd_emit<<<(d.n * 3 + 3) / 4, 128, 0, st>>>(d, b.candcount, b.candseg, b.candok, b.rawseg, b.segcount);
+    k_lsd_emit<<<d.n * 3, 128, 0, st>>>(d, b.candcount, b.candseg, b.candok, b.candrank, b.rawseg, b.segcount);
     ++g_launches;
 }
 

@@ -193,6 +193,10 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     CKC(dalloc(&b.scs, n * 3 * ctx->pixcap));
     CKC(dalloc(&b.usedbits, n * 3 * (size_t)((ctx->pixcap + 31) / 32)));
     CKC(dalloc(&b.order, n * 3 * ctx->pixcap));
+    CKC(dalloc(&b.label, n * 3 * ctx->pixcap)); CKC(dalloc(&b.csize, n * 3 * ctx->pixcap)); CKC(dalloc(&b.coff, n * 3 * ctx->pixcap));
+    CKC(dalloc(&b.corder, n * 3 * ctx->pixcap)); CKC(dalloc(&b.cpos, n * 3 * ctx->pixcap));
+    CKC(dalloc(&b.tasks, n * 3 * 256)); CKC(dalloc(&b.worklist, n * 3 * 256)); CKC(dalloc(&b.taskctr, 64 * 4));
+    CKC(dalloc(&b.candrank, n * 3 * ctx->segcap));
     CKC(dalloc(&b.reg, n * 3 * ctx->pixcap * 2));
     CKC(dalloc(&b.pixcount, n * 3));
     CKC(dalloc(&b.g2max, n * 3));
@@ -226,7 +230,7 @@ extern "C" void lsf_destroy(lsf_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     Buffers &b = ctx->b;
-    void *ptrs[] = {b.src, b.planesA, b.planesB, b.gray, b.dx, b.lsdw, b.pix, b.pxy, b.fat, b.scs, b.usedbits, b.order, b.reg, b.pixcount,
+    void *ptrs[] = {b.src, b.planesA, b.planesB, b.gray, b.dx, b.lsdw, b.pix, b.pxy, b.fat, b.scs, b.usedbits, b.order, b.label, b.csize, b.coff, b.corder, b.cpos, b.tasks, b.worklist, b.taskctr, b.candrank, b.reg, b.pixcount,
                     b.g2max, b.rawseg, b.cand, b.candcount, b.candlist, b.candseg, b.candok, b.segcount, b.frame_off, b.flags, b.o_color, b.o_lines, b.o_normals, b.o_centers,
                     b.o_pixn, b.o_nf32, b.o_ground, b.o_keep, b.o_desc, b.o_frame, b.o_midx, b.o_mdist, ctx->map,
                     ctx->knn_scratch, ctx->tap_tmp, ctx->seg_in, ctx->carry};
@@ -391,6 +395,7 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
     if (getenv("LSF_CHUNK_FRAMES")) chunk = atoi(getenv("LSF_CHUNK_FRAMES"));
     if (chunk == 0) chunk = n >= 64 ? std::max(32, (n + 7) / 8) : n;
     if (chunk < 0 || chunk > n || (d.debug & 2)) chunk = n;
+    if ((n + chunk - 1) / chunk > 64) chunk = (n + 63) / 64;
     const int nchunks = (n + chunk - 1) / chunk;
     const bool host_in = mem_kind != LSF_MEM_DEVICE;
     const u8 *src;
@@ -403,6 +408,7 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
     ctx->last_src = src; ctx->d = d; ctx->have_batch = true;
     if (d.identity_geom) make_tma(ctx, src, n, src_h, src_w, d.src_pitch); else ctx->tma.valid = 0;
     CK(cudaMemsetAsync(b.flags, 0, 4 * sizeof(int), ctx->st));
+    CK(cudaMemsetAsync(b.taskctr, 0, 64 * 4 * sizeof(int), ctx->st));
     if (nchunks == 1) {
         if (host_in) {
             CK(cudaMemcpy2DAsync(b.src, d.src_pitch, bgr, pitch, (size_t)src_w * 3, (size_t)src_h * n, cudaMemcpyHostToDevice, ctx->st));
@@ -453,6 +459,9 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
             bc.fat += i0 * d.pixcap * 40; bc.order += i0 * d.pixcap; bc.reg += i0 * 2 * d.pixcap;
             bc.usedbits += i0 * (size_t)((d.pixcap + 31) / 32);
             bc.pixcount += i0; bc.g2max += i0; bc.cand += i0 * d.segcap; bc.candcount += i0;
+            bc.label += i0 * d.pixcap; bc.csize += i0 * d.pixcap; bc.coff += i0 * d.pixcap; bc.corder += i0 * d.pixcap;
+            bc.cpos += i0 * d.pixcap; bc.tasks += i0 * 256; bc.worklist += i0 * 256; bc.taskctr += 4 * c;
+            bc.candrank += i0 * d.segcap;
             launch_color_canny(dc, ctx->cp, src + (size_t)f0 * d.src_frame, ctx->tma, bc.planesA, bc.gray, cs);
             launch_hysteresis(dc, ctx->cfg.dilation_kernel_size, bc.planesA, bc.planesB, cs);
             launch_lsd_pre(dc, bc.planesB, bc, cs);
