@@ -150,6 +150,13 @@ LSF_API int lsf_set_chunk_frames(lsf_ctx *ctx, int chunk_frames);
 LSF_API int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int src_h, int src_w, size_t pitch,
                                 int mem_kind, int stages, int k, lsf_segments *out);
 
+/* Streaming replay: start the host->device copy of the NEXT batch of host frames now (returns immediately; the copy
+ * runs on the ctx's copy stream into the spare staging buffer) so that it overlaps the kernels of the batch being
+ * processed.  A following lsf_front_end_batch call with the same `bgr` pointer and geometry consumes the staged
+ * frames instead of copying again; up to two batches may be staged ahead.  The caller must keep `bgr` (pinned
+ * memory for a truly asynchronous copy) unchanged until that call returns. */
+LSF_API int lsf_prefetch_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int src_h, int src_w, size_t pitch);
+
 /* = lsf_front_end_batch(..., LSF_STAGE_DETECT, 0, out) */
 LSF_API int lsf_detect_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int src_h, int src_w, size_t pitch,
                              int mem_kind, lsf_segments *out);

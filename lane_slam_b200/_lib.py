@@ -40,7 +40,7 @@ class LsfSegments(C.Structure):
 
 _EXPORTS = [
     "lsf_default_config", "lsf_create", "lsf_destroy", "lsf_last_error", "lsf_set_color_transform", "lsf_set_chunk_frames",
-    "lsf_front_end_batch", "lsf_detect_batch", "lsf_describe_batch", "lsf_project_filter_batch",
+    "lsf_front_end_batch", "lsf_prefetch_batch", "lsf_detect_batch", "lsf_describe_batch", "lsf_project_filter_batch",
     "lsf_knn_hamming", "lsf_map_clear", "lsf_map_add", "lsf_map_size", "lsf_reset_sequence", "lsf_get_tap", "lsf_image_dims",
     "lsf_last_timings", "lsf_launch_count", "lsf_stream", "lsf_version",
 ]
@@ -73,6 +73,7 @@ def load():
     lib.lsf_set_color_transform.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.lsf_set_chunk_frames.argtypes = [vp, i32]
     lib.lsf_front_end_batch.argtypes = [vp, vp, i32, i32, i32, sz, i32, i32, i32, C.POINTER(LsfSegments)]
+    lib.lsf_prefetch_batch.argtypes = [vp, vp, i32, i32, i32, sz]
     lib.lsf_detect_batch.argtypes = [vp, vp, i32, i32, i32, sz, i32, C.POINTER(LsfSegments)]
     lib.lsf_describe_batch.argtypes = [vp, C.POINTER(LsfSegments)]
     lib.lsf_project_filter_batch.argtypes = [vp, vp, vp, i32, i32, vp, vp]

@@ -35,8 +35,8 @@ struct Dims {
     int identity_geom;     // 1: no resize (dh==src_h, dw==src_w)
     int identity_color;    // 1: AntiInstagram scale==1, shift==0
     int debug;             // LSF_TRACE_LSD: bit 0 device printf of every LSD candidate, bit 1 grow cycle counters
-    int f0;                // first frame of this launch inside the batch (TMA coordinate; every other buffer is pre-offset)
-    int img0;              // = 3 * f0: first colour image of this launch (absolute ids in the candidate work list)
+    int f0;                // first frame of this launch inside the batch (TMA coordinate, frame ids of the output rows;
+                           // every per-frame / per-image buffer is pre-offset to the chunk)
 };
 
 // one entry per 32 scaled pixels: defined-angle bits + number of defined pixels before this word
@@ -87,7 +87,7 @@ struct Buffers {
     u32 *corder, *cpos; // [n*3][pixcap]  seed order partitioned by component; position of each entry in order[]
     uint2 *tasks;       // [n*3][256]     {offset into corder, size} of every component with >= min_reg pixels
     uint2 *worklist;    // [n*3*256]      (image, task) work list of the growing kernel: big tasks from the front, small from the back
-    int *taskctr;       // [64][4]        per pipeline chunk: big tasks, small tasks, work cursor
+    int *taskctr;       // [64][4]        per pipeline chunk: big tasks, small tasks, work cursor, candidates
     u32 *candrank;      // [n*3][segcap]  position of the candidate's seed in order[] (restores the acceptance order)
     uint4 *reg;         // [n*3][2*pixcap] region point list {idx, xy, g2, angle bits} + scratch
     u32 *usedbits;      // [n*3][ceil(pixcap/32)] USED bitmap, only when it does not fit in shared memory
@@ -100,7 +100,8 @@ struct Buffers {
     u8 *candok;         // [n*3][segcap]  1 iff NFA accepted
     LsdSeg *rawseg;     // [n*3][segcap]
     int *segcount;      // [n*3]
-    int *frame_off;     // [n+1]
+    int *frame_off;     // [n+1]          first output row of every frame (global: chunks chain through it)
+    int *imgoff;        // [n*3]          first output row of every colour image
     int *flags;         // [4] 0 pix overflow, 1 seg/candidate overflow, 2 out capacity, 3 candidate counter
     // compacted per-segment outputs (capacity outcap)
     int outcap;
@@ -117,17 +118,18 @@ void launch_hysteresis(const Dims &d, int dilate, const u32 *planesA, u32 *plane
 void launch_lsd_pre(const Dims &d, const u32 *planesB, Buffers &b, cudaStream_t st);
 void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st);      // seeds + region growing + refine
 void launch_lsd_validate(const Dims &d, Buffers &b, cudaStream_t st);  // NFA validation + emit
+void launch_seg_offsets(const Dims &d, Buffers &b, cudaStream_t st);
 void launch_segments(const Dims &d, const CamParams &cam, Buffers &b, int do_ground, cudaStream_t st);
 void launch_gray_sobel(const Dims &d, const u8 *gray, short *dx, short *dy, cudaStream_t st);
-void launch_lbd(const Dims &d, const float *lines, const int *frame_of_seg, int nseg_cap, const int *nseg_dev,
-                const short *dx, const short *dy, u8 *desc, cudaStream_t st);
+void launch_lbd(const Dims &d, const float *lines, const int *frame_of_seg, int nseg_cap, const int *seg_lo_dev,
+                const int *seg_hi_dev, const short *dx, const short *dy, u8 *desc, cudaStream_t st);
 void launch_project_filter(const CamParams &cam, const float *pixn, const u8 *color, int nseg, double *ground, u8 *keep,
                            cudaStream_t st);
 void launch_knn(const u8 *q, int nq_cap, const int *nq_dev, const u8 *m, int nm, int k, int max_dist, int *idx, int *dist,
                 void *scratch, size_t scratch_bytes, cudaStream_t st);
 size_t knn_scratch_bytes(int nq, int nm, int k);
-void launch_knn_prev(const u8 *desc, const int *frame_off, int n, int k, int max_dist, const u8 *carry, int carry_n, int *idx,
-                     int *dist, cudaStream_t st);
+void launch_knn_prev(const u8 *desc, const int *frame_off, int f_begin, int n, int k, int max_dist, const u8 *carry, int carry_n,
+                     int *idx, int *dist, cudaStream_t st);
 void launch_unpack_plane(const u32 *plane, int h, int w, int wp, u8 *dst, cudaStream_t st);
 void launch_labels_tap(const u32 *planesA_frame, int h, int w, int wp, u8 *dst, cudaStream_t st);
 void launch_image_tap(const Dims &d, const ColorParams &cp, const u8 *src_frame, u8 *dst, cudaStream_t st);

@@ -97,12 +97,12 @@ __global__ void k_knn_merge(int nq_cap, const int *__restrict__ nq_dev, int nspl
 // per frame; frame 0 matches the carry (last frame of the previous batch).  trainIdx is the index inside
 // the previous frame's segment list.
 template <int K>
-__global__ void __launch_bounds__(128) k_knn_prev(const uint4 *__restrict__ desc, const int *__restrict__ frame_off, int k, int max_dist,
+__global__ void __launch_bounds__(128) k_knn_prev(const uint4 *__restrict__ desc, const int *__restrict__ frame_off, int f_begin, int k, int max_dist,
                                                  const uint4 *__restrict__ carry, int carry_n, int *__restrict__ idx,
                                                  int *__restrict__ dist)
 {
     __shared__ uint4 tile[128 * 2];
-    const int f = blockIdx.x;
+    const int f = f_begin + blockIdx.x;
     const int q0 = frame_off[f], q1 = frame_off[f + 1];
     const uint4 *tp; int nt;
     if (f > 0) { int t0 = frame_off[f - 1]; tp = desc + 2 * (size_t)t0; nt = q0 - t0; }
@@ -136,14 +136,14 @@ __global__ void __launch_bounds__(128) k_knn_prev(const uint4 *__restrict__ desc
     }
 }
 
-void launch_knn_prev(const u8 *desc, const int *frame_off, int n, int k, int max_dist, const u8 *carry, int carry_n, int *idx,
-                     int *dist, cudaStream_t st)
+void launch_knn_prev(const u8 *desc, const int *frame_off, int f_begin, int n, int k, int max_dist, const u8 *carry, int carry_n,
+                     int *idx, int *dist, cudaStream_t st)
 {
     const uint4 *d4 = (const uint4 *)desc, *c4 = (const uint4 *)carry;
-    if (k <= 1) k_knn_prev<1><<<n, 128, 0, st>>>(d4, frame_off, k, max_dist, c4, carry_n, idx, dist);
-    else if (k <= 2) k_knn_prev<2><<<n, 128, 0, st>>>(d4, frame_off, k, max_dist, c4, carry_n, idx, dist);
-    else if (k <= 4) k_knn_prev<4><<<n, 128, 0, st>>>(d4, frame_off, k, max_dist, c4, carry_n, idx, dist);
-    else k_knn_prev<8><<<n, 128, 0, st>>>(d4, frame_off, k, max_dist, c4, carry_n, idx, dist);
+    if (k <= 1) k_knn_prev<1><<<n, 128, 0, st>>>(d4, frame_off, f_begin, k, max_dist, c4, carry_n, idx, dist);
+    else if (k <= 2) k_knn_prev<2><<<n, 128, 0, st>>>(d4, frame_off, f_begin, k, max_dist, c4, carry_n, idx, dist);
+    else if (k <= 4) k_knn_prev<4><<<n, 128, 0, st>>>(d4, frame_off, f_begin, k, max_dist, c4, carry_n, idx, dist);
+    else k_knn_prev<8><<<n, 128, 0, st>>>(d4, frame_off, f_begin, k, max_dist, c4, carry_n, idx, dist);
     ++g_launches;
 }
 

@@ -93,15 +93,17 @@ static void ensure_lbd_tables()
 constexpr int LBD_WARPS = 4;
 
 __global__ void __launch_bounds__(LBD_WARPS * 32) k_lbd(Dims d, const float *__restrict__ lines, const int *__restrict__ frame_of_seg,
-                                                       int nseg_cap, const int *__restrict__ nseg_dev,
+                                                       int nseg_cap, const int *__restrict__ seg_lo_dev,
+                                                       const int *__restrict__ seg_hi_dev,
                                                        const short2 *__restrict__ dxy, u8 *__restrict__ desc)
 {
     __shared__ float rows[LBD_WARPS][63][4];   // per-row sums scaled by the global Gaussian weight
     __shared__ float dvec[LBD_WARPS][72];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nseg = min(*nseg_dev, nseg_cap);
+    const int seg_lo = seg_lo_dev ? *seg_lo_dev : 0;
+    const int nseg = min(*seg_hi_dev, nseg_cap);
     const int W = d.w, H = d.h;
-    for (int sidx = blockIdx.x * LBD_WARPS + warp; sidx < nseg; sidx += gridDim.x * LBD_WARPS) {
+    for (int sidx = seg_lo + blockIdx.x * LBD_WARPS + warp; sidx < nseg; sidx += gridDim.x * LBD_WARPS) {
         // ---- KeyLine fill (octave 0) ----
         float4 ln = reinterpret_cast<const float4 *>(lines)[sidx];
         float e0 = ln.x, e1 = ln.y, e2 = ln.z, e3 = ln.w;
@@ -217,14 +219,14 @@ __global__ void __launch_bounds__(LBD_WARPS * 32) k_lbd(Dims d, const float *__r
     }
 }
 
-void launch_lbd(const Dims &d, const float *lines, const int *frame_of_seg, int nseg_cap, const int *nseg_dev, const short *dx,
-                const short *, u8 *desc, cudaStream_t st)
+void launch_lbd(const Dims &d, const float *lines, const int *frame_of_seg, int nseg_cap, const int *seg_lo_dev,
+                const int *seg_hi_dev, const short *dx, const short *, u8 *desc, cudaStream_t st)
 {
     ensure_lbd_tables();
     int grid = 148 * 4;
     if (nseg_cap < grid * LBD_WARPS) grid = (nseg_cap + LBD_WARPS - 1) / LBD_WARPS;
     if (grid < 1) grid = 1;
-    k_lbd<<<grid, LBD_WARPS * 32, 0, st>>>(d, lines, frame_of_seg, nseg_cap, nseg_dev, reinterpret_cast<const short2 *>(dx), desc);
+    k_lbd<<<grid, LBD_WARPS * 32, 0, st>>>(d, lines, frame_of_seg, nseg_cap, seg_lo_dev, seg_hi_dev, reinterpret_cast<const short2 *>(dx), desc);
     ++g_launches;
 }
 

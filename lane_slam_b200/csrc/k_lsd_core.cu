@@ -1030,8 +1030,8 @@ __global__ void __launch_bounds__(32) k_lsd_grow(Dims d, const LsdWord *__restri
                         c.width = rec.width; c.theta = rec.theta; c.dx = rec.dx; c.dy = rec.dy;
                         out[slot] = c;
                         orank[slot] = srank;
-                        const int gs = atomicAdd(&flags[3], 1);
-                        candlist[gs] = make_uint2((u32)(img + d.img0), (u32)slot);
+                        const int gs = atomicAdd(&taskctr[3], 1);
+                        candlist[gs] = make_uint2((u32)img, (u32)slot);
                     } else {
                         atomicMax(&flags[1], slot + 1);
                     }
@@ -1051,11 +1051,11 @@ constexpr int VAL_WARPS = 4;
 
 __global__ void __launch_bounds__(VAL_WARPS * 32, 6) k_lsd_validate(Dims d, const LsdWord *__restrict__ lsdw, const LsdPix *__restrict__ pix,
                                                                    const int *__restrict__ pixcount, const LsdCand *__restrict__ cand,
-                                                                const uint2 *__restrict__ candlist, const int *__restrict__ flags,
+                                                                const uint2 *__restrict__ candlist, const int *__restrict__ taskctr,
                                                                 LsdSeg *__restrict__ candseg, u8 *__restrict__ candok)
 {
     const int lane = threadIdx.x & 31;
-    const int total = min(flags[3], d.n * 3 * d.segcap);
+    const int total = min(taskctr[3], d.n * 3 * d.segcap);
     const int nwarps = gridDim.x * VAL_WARPS;
     for (int t = blockIdx.x * VAL_WARPS + (threadIdx.x >> 5); t < total; t += nwarps) {
         uint2 e = candlist[t];
@@ -1174,7 +1174,7 @@ void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st)
 
 void launch_lsd_validate(const Dims &d, Buffers &b, cudaStream_t st)
 {
-    k_lsd_validate<<<148 * 6, VAL_WARPS * 32, 0, st>>>(d, b.lsdw, b.pix, b.pixcount, b.cand, b.candlist, b.flags, b.candseg, b.candok);
+    k_lsd_validate<<<148 * 6, VAL_WARPS * 32, 0, st>>>(d, b.lsdw, b.pix, b.pixcount, b.cand, b.candlist, b.taskctr, b.candseg, b.candok);
     ++g_launches;
     k_lsd_emit<<<d.n * 3, 128, 0, st>>>(d, b.candcount, b.candseg, b.candok, b.candrank, b.rawseg, b.segcount);
     ++g_launches;

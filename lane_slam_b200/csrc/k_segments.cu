@@ -10,13 +10,16 @@
 namespace lsf {
 
 // ---- exclusive scan of segcount[n*3] -> imgoff[n*3], frame_off[n+1] (single block) ----
-__global__ void __launch_bounds__(1024) k_seg_offsets(int nimg, const int *__restrict__ segcount, int *__restrict__ imgoff,
-                                                     int *__restrict__ frame_off, int outcap, int *__restrict__ flags)
+// A pipeline chunk continues where the previous one ended: frame_off points at the chunk's first frame and,
+// unless this is the first chunk, frame_off[0] already holds the previous chunk's end.
+__global__ void __launch_bounds__(1024) k_seg_offsets(int nimg, int first_chunk, const int *__restrict__ segcount,
+                                                     int *__restrict__ imgoff, int *__restrict__ frame_off, int outcap,
+                                                     int *__restrict__ flags)
 {
     __shared__ int wtot[32];
     __shared__ int carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry = 0;
+    if (tid == 0) carry = first_chunk ? 0 : frame_off[0];
     __syncthreads();
     for (int base = 0; base < nimg; base += 1024) {
         int i = base + tid;
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(128) k_segments(Dims d, CamParams cam, int do_
     double flag = __dsub_rn(__dmul_rn((double)(x2 - x1), ny), __dmul_rn((double)(y2 - y1), nx));
     if (flag > 0) { float t = x1; x1 = x2; x2 = t; t = y1; y1 = y2; y2 = t; }
     o_color[o] = (u8)c;
-    o_frame[o] = f;
+    o_frame[o] = f + d.f0;
     reinterpret_cast<float4 *>(o_lines)[o] = make_float4(x1, y1, x2, y2);
     reinterpret_cast<double2 *>(o_normals)[o] = make_double2(nx, ny);
     reinterpret_cast<float2 *>(o_centers)[o] = make_float2(cx, cy);
@@ -154,14 +157,16 @@ __global__ void __launch_bounds__(128) k_segments(Dims d, CamParams cam, int do_
     }
 }
 
+void launch_seg_offsets(const Dims &d, Buffers &b, cudaStream_t st)
+{
+    k_seg_offsets<<<1, 1024, 0, st>>>(d.n * 3, d.f0 == 0, b.segcount, b.imgoff, b.frame_off, b.outcap, b.flags);
+    ++g_launches;
+}
+
 void launch_segments(const Dims &d, const CamParams &cam, Buffers &b, int do_ground, cudaStream_t st)
 {
-    // imgoff lives in the tail of frame_off's allocation: frame_off[n+1], imgoff[n*3]
-    int *imgoff = b.frame_off + (d.n + 1);
-    k_seg_offsets<<<1, 1024, 0, st>>>(d.n * 3, b.segcount, imgoff, b.frame_off, b.outcap, b.flags);
-    ++g_launches;
     dim3 grid((d.segcap + 127) / 128, d.n * 3);
-    k_segments<<<grid, 128, 0, st>>>(d, cam, do_ground, b.rawseg, b.segcount, imgoff, b.planesB, b.outcap, b.o_color, b.o_lines,
+    k_segments<<<grid, 128, 0, st>>>(d, cam, do_ground, b.rawseg, b.segcount, b.imgoff, b.planesB, b.outcap, b.o_color, b.o_lines,
                                      b.o_normals, b.o_centers, b.o_pixn, b.o_nf32, b.o_ground, b.o_keep, b.o_frame);
     ++g_launches;
 }

@@ -45,10 +45,15 @@ struct lsf_ctx {
     // TMA
     TmaDesc tma;
     const u8 *tma_src; int tma_n, tma_h, tma_w; size_t tma_pitch;
+    // staged input: two staging buffers; a prefetch (lsf_prefetch_batch) fills one while the other is being processed
+    struct Staged { const u8 *host; int n, h, w; size_t pitch; cudaEvent_t ev; bool valid; unsigned long long seq; };
+    u8 *stage_buf[2];
+    Staged staged[2];
+    unsigned long long stage_seq;
     // chunk pipeline: copy stream, compute streams, per-chunk events
     cudaStream_t copy_st;
-    cudaStream_t aux[4];
-    std::vector<cudaEvent_t> ev_copy, ev_done;
+    cudaStream_t aux[8];
+    std::vector<cudaEvent_t> ev_copy, ev_done, ev_off, ev_lbd;
     cudaEvent_t ev_begin;
     // timing
     std::vector<StageTime> events;
@@ -139,7 +144,9 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     ctx->tma.valid = 0; ctx->tma_src = nullptr;
     ctx->n_events = 0;
     ctx->copy_st = nullptr; ctx->ev_begin = nullptr;
-    for (int i = 0; i < 4; ++i) ctx->aux[i] = nullptr;
+    ctx->stage_buf[0] = ctx->stage_buf[1] = nullptr; ctx->stage_seq = 0;
+    for (int i = 0; i < 2; ++i) { ctx->staged[i].valid = false; ctx->staged[i].ev = nullptr; }
+    for (int i = 0; i < 8; ++i) ctx->aux[i] = nullptr;
     ctx->carry = nullptr; ctx->carry_n = 0; ctx->carry_cap = 0; ctx->h_small = nullptr; ctx->st = nullptr;
     memset(&ctx->b, 0, sizeof(ctx->b));
     auto bail = [&](int code, const std::string &msg) { g_create_error = msg; lsf_destroy(ctx); return code; };
@@ -151,7 +158,7 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     CKC(cudaSetDevice(ctx->device));
     CKC(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking));
-    for (int i = 0; i < 4; ++i) CKC(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) CKC(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
     CKC(cudaEventCreateWithFlags(&ctx->ev_begin, cudaEventDisableTiming));
     ctx->max_batch = cfg->max_batch > 0 ? cfg->max_batch : 1;
     ctx->max_src_h = cfg->max_src_h > 0 ? cfg->max_src_h : cfg->img_h;
@@ -181,6 +188,8 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     const size_t n = ctx->max_batch, N = (size_t)ctx->h * ctx->w, ps = (size_t)ctx->h * ctx->wp;
     Buffers &b = ctx->b;
     CKC(dalloc(&b.src, n * ctx->max_src_h * ctx->max_src_w * 3));
+    ctx->stage_buf[0] = b.src;
+    for (int i = 0; i < 2; ++i) CKC(cudaEventCreateWithFlags(&ctx->staged[i].ev, cudaEventDisableTiming));
     CKC(dalloc(&b.planesA, n * PA_COUNT * ps));
     CKC(dalloc(&b.planesB, n * PB_COUNT * ps));
     CKC(dalloc(&b.gray, n * N));
@@ -208,6 +217,7 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     CKC(dalloc(&b.candok, n * 3 * ctx->segcap));
     CKC(dalloc(&b.segcount, n * 3));
     CKC(dalloc(&b.frame_off, (n + 1) + n * 3));
+    b.imgoff = b.frame_off + (n + 1);
     CKC(dalloc(&b.flags, 4));
     b.outcap = (int)std::min<size_t>(n * 3 * ctx->segcap, (size_t)1 << 30);
     const size_t oc = b.outcap;
@@ -230,18 +240,22 @@ extern "C" void lsf_destroy(lsf_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     Buffers &b = ctx->b;
-    void *ptrs[] = {b.src, b.planesA, b.planesB, b.gray, b.dx, b.lsdw, b.pix, b.pxy, b.fat, b.scs, b.usedbits, b.order, b.label, b.csize, b.coff, b.corder, b.cpos, b.tasks, b.worklist, b.taskctr, b.candrank, b.reg, b.pixcount,
+    void *ptrs[] = {ctx->stage_buf[0], b.planesA, b.planesB, b.gray, b.dx, b.lsdw, b.pix, b.pxy, b.fat, b.scs, b.usedbits, b.order, b.label, b.csize, b.coff, b.corder, b.cpos, b.tasks, b.worklist, b.taskctr, b.candrank, b.reg, b.pixcount,
                     b.g2max, b.rawseg, b.cand, b.candcount, b.candlist, b.candseg, b.candok, b.segcount, b.frame_off, b.flags, b.o_color, b.o_lines, b.o_normals, b.o_centers,
                     b.o_pixn, b.o_nf32, b.o_ground, b.o_keep, b.o_desc, b.o_frame, b.o_midx, b.o_mdist, ctx->map,
                     ctx->knn_scratch, ctx->tap_tmp, ctx->seg_in, ctx->carry};
     for (void *p : ptrs) if (p) cudaFree(p);
+    if (ctx->stage_buf[1]) cudaFree(ctx->stage_buf[1]);
+    for (int i = 0; i < 2; ++i) if (ctx->staged[i].ev) cudaEventDestroy(ctx->staged[i].ev);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
     for (auto &e : ctx->events) cudaEventDestroy(e.ev);
     for (auto &e : ctx->ev_copy) cudaEventDestroy(e);
     for (auto &e : ctx->ev_done) cudaEventDestroy(e);
+    for (auto &e : ctx->ev_off) cudaEventDestroy(e);
+    for (auto &e : ctx->ev_lbd) cudaEventDestroy(e);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->copy_st) cudaStreamDestroy(ctx->copy_st);
-    for (int i = 0; i < 4; ++i) if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
+    for (int i = 0; i < 8; ++i) if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
     if (ctx->st) cudaStreamDestroy(ctx->st);
     delete ctx;
 }
@@ -344,6 +358,24 @@ extern "C" long long lsf_launch_count(const lsf_ctx *ctx) { return ctx ? g_launc
 extern "C" void *lsf_stream(lsf_ctx *ctx) { return ctx ? (void *)ctx->st : nullptr; }
 extern "C" const char *lsf_version(void) { return "lsf 0.1 (sm_100a)"; }
 
+extern "C" int lsf_prefetch_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int src_h, int src_w, size_t pitch)
+{
+    if (!ctx) return LSF_E_ARG;
+    if (!bgr || n <= 0 || n > ctx->max_batch || src_h <= 0 || src_w <= 0 || src_h > ctx->max_src_h || src_w > ctx->max_src_w ||
+        pitch < (size_t)src_w * 3)
+        return fail(ctx, LSF_E_ARG, "lsf_prefetch_batch: bad frames / geometry");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->stage_buf[1]) CK(cudaMalloc((void **)&ctx->stage_buf[1], (size_t)ctx->max_batch * ctx->max_src_h * ctx->max_src_w * 3));
+    // the staging buffer that is not holding an unconsumed batch; the oldest one if both do
+    int slot = !ctx->staged[0].valid ? 0 : !ctx->staged[1].valid ? 1 : (ctx->staged[0].seq < ctx->staged[1].seq ? 0 : 1);
+    lsf_ctx::Staged &sg = ctx->staged[slot];
+    CK(cudaMemcpy2DAsync(ctx->stage_buf[slot], (size_t)src_w * 3, bgr, pitch, (size_t)src_w * 3, (size_t)src_h * n, cudaMemcpyHostToDevice,
+                         ctx->copy_st));
+    CK(cudaEventRecord(sg.ev, ctx->copy_st));
+    sg.host = bgr; sg.n = n; sg.h = src_h; sg.w = src_w; sg.pitch = pitch; sg.valid = true; sg.seq = ++ctx->stage_seq;
+    return LSF_OK;
+}
+
 static cudaMemcpyKind out_kind(int mem) { return mem == LSF_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost; }
 
 static int ensure_knn(lsf_ctx *ctx, int nq, int nm, int k)
@@ -388,98 +420,136 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
     d.identity_color = 1;
     for (int i = 0; i < 3; ++i) if (ctx->cp.ai_scale[i] != 1.f || ctx->cp.ai_shift[i] != 0.f) d.identity_color = 0;
 
-    d.f0 = 0; d.img0 = 0;
+    d.f0 = 0;
     ctx->n_events = 0;
     mark(ctx, "start");
     int chunk = ctx->cfg.chunk_frames;
     if (getenv("LSF_CHUNK_FRAMES")) chunk = atoi(getenv("LSF_CHUNK_FRAMES"));
-    if (chunk == 0) chunk = n >= 64 ? std::max(32, (n + 7) / 8) : n;
-    if (chunk < 0 || chunk > n || (d.debug & 2)) chunk = n;
-    if ((n + chunk - 1) / chunk > 64) chunk = (n + 63) / 64;
-    const int nchunks = (n + chunk - 1) / chunk;
     const bool host_in = mem_kind != LSF_MEM_DEVICE;
+    // automatic: host frames -> 8 chunks (the copy of chunk c+1 hides behind the kernels of chunk c);
+    // device frames -> 2 chunks (only the latency-bound LSD search of one half overlaps the dense kernels of the other)
+    if (chunk == 0) chunk = n >= 64 ? (host_in ? std::max(16, (n + 7) / 8) : (n + 1) / 2) : n;
+    const bool auto_chunk = ctx->cfg.chunk_frames == 0 && !getenv("LSF_CHUNK_FRAMES");
     const u8 *src;
+    bool staged_hit = false;
     if (!host_in) {
         src = bgr; d.src_pitch = pitch; d.src_frame = pitch * src_h;
     } else {
         d.src_pitch = (size_t)src_w * 3; d.src_frame = d.src_pitch * src_h;
+        // frames staged ahead by lsf_prefetch_batch (oldest matching one)?
+        int hit = -1;
+        for (int i = 0; i < 2; ++i) {
+            const lsf_ctx::Staged &sg = ctx->staged[i];
+            if (sg.valid && sg.host == bgr && sg.n == n && sg.h == src_h && sg.w == src_w && sg.pitch == pitch &&
+                (hit < 0 || sg.seq < ctx->staged[hit].seq))
+                hit = i;
+        }
+        if (hit >= 0) {
+            staged_hit = true;
+            if (auto_chunk && n >= 64) chunk = (n + 1) / 2;     // the frames are already on the device
+            b.src = ctx->stage_buf[hit];
+            ctx->staged[hit].valid = false;
+            CK(cudaStreamWaitEvent(ctx->st, ctx->staged[hit].ev, 0));
+        } else {
+            // copy now, into a staging buffer that holds nothing staged (drop the oldest staged batch if both do)
+            int slot = !ctx->staged[0].valid ? 0 : (ctx->stage_buf[1] && !ctx->staged[1].valid) ? 1 : 0;
+            if (ctx->staged[slot].valid) { CK(cudaStreamSynchronize(ctx->copy_st)); ctx->staged[slot].valid = false; }
+            b.src = ctx->stage_buf[slot];
+        }
         src = b.src;
     }
+    if (chunk < 0 || chunk > n || (d.debug & 2)) chunk = n;
+    if ((n + chunk - 1) / chunk > 64) chunk = (n + 63) / 64;
+    const int nchunks = (n + chunk - 1) / chunk;
     ctx->last_src = src; ctx->d = d; ctx->have_batch = true;
     if (d.identity_geom) make_tma(ctx, src, n, src_h, src_w, d.src_pitch); else ctx->tma.valid = 0;
     CK(cudaMemsetAsync(b.flags, 0, 4 * sizeof(int), ctx->st));
     CK(cudaMemsetAsync(b.taskctr, 0, 64 * 4 * sizeof(int), ctx->st));
-    if (nchunks == 1) {
-        if (host_in) {
-            CK(cudaMemcpy2DAsync(b.src, d.src_pitch, bgr, pitch, (size_t)src_w * 3, (size_t)src_h * n, cudaMemcpyHostToDevice, ctx->st));
-            mark(ctx, "h2d");
-        }
-        launch_color_canny(d, ctx->cp, src, ctx->tma, b.planesA, b.gray, ctx->st);
-        mark(ctx, "color_canny");
-        launch_hysteresis(d, ctx->cfg.dilation_kernel_size, b.planesA, b.planesB, ctx->st);
-        mark(ctx, "hysteresis_dilate");
-        launch_lsd_pre(d, b.planesB, b, ctx->st);
-        mark(ctx, "lsd_pre");
-        launch_lsd_core(d, b, ctx->st);
-        mark(ctx, "lsd_grow");
-        if (stages & LSF_STAGE_DESCRIBE) {
-            launch_gray_sobel(d, b.gray, b.dx, nullptr, ctx->st);
-            mark(ctx, "gray_sobel");
-        }
-    } else {
+    const bool describe = (stages & LSF_STAGE_DESCRIBE) != 0, match_prev = (stages & LSF_STAGE_MATCH_PREV) != 0;
+    if (match_prev) {
+        if (!b.o_midx) { CK(dalloc(&b.o_midx, (size_t)b.outcap * 8)); CK(dalloc(&b.o_mdist, (size_t)b.outcap * 8)); }
+        if (!ctx->carry) { ctx->carry_cap = 3 * ctx->segcap; CK(cudaMalloc((void **)&ctx->carry, (size_t)ctx->carry_cap * 32)); }
+    }
+    const size_t ps = (size_t)d.h * d.wp, N = (size_t)d.h * d.w;
+    const bool piped = nchunks > 1;
+    if (piped) {
         // Chunk pipeline: chunk c is copied on the copy stream while earlier chunks compute on the aux streams
-        // (round robin).  The region-growing kernel is a long chain of dependent steps that leaves the SMs
-        // mostly idle, so it overlaps with the dense kernels of the following chunks.
+        // (round robin).  The region-growing kernel is a chain of dependent steps that leaves issue slots free,
+        // so it overlaps with the dense kernels of other chunks.  Two scalars chain the chunks: the output row
+        // where a chunk starts (seg_offsets) and the previous frame's descriptors (frame-to-frame matching).
         while ((int)ctx->ev_copy.size() < nchunks) {
-            cudaEvent_t e0, e1;
-            CK(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
-            ctx->ev_copy.push_back(e0); ctx->ev_done.push_back(e1);
+            cudaEvent_t e[4];
+            for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&e[i], cudaEventDisableTiming));
+            ctx->ev_copy.push_back(e[0]); ctx->ev_done.push_back(e[1]); ctx->ev_off.push_back(e[2]); ctx->ev_lbd.push_back(e[3]);
         }
-        CK(cudaEventRecord(ctx->ev_begin, ctx->st));     // after the flags reset (and everything of the previous call)
+        CK(cudaEventRecord(ctx->ev_begin, ctx->st));     // after the resets (and everything of the previous call)
         CK(cudaStreamWaitEvent(ctx->copy_st, ctx->ev_begin, 0));
-        for (int i = 0; i < 4; ++i) CK(cudaStreamWaitEvent(ctx->aux[i], ctx->ev_begin, 0));
-        const size_t ps = (size_t)d.h * d.wp, N = (size_t)d.h * d.w;
-        for (int c = 0; c < nchunks; ++c) {
-            const int f0 = c * chunk, nc = std::min(chunk, n - f0);
-            cudaStream_t cs = ctx->aux[c & 3];
-            if (host_in) {
-                CK(cudaMemcpy2DAsync(b.src + (size_t)f0 * d.src_frame, d.src_pitch, bgr + (size_t)f0 * pitch * src_h, pitch,
-                                     (size_t)src_w * 3, (size_t)src_h * nc, cudaMemcpyHostToDevice, ctx->copy_st));
-                CK(cudaEventRecord(ctx->ev_copy[c], ctx->copy_st));
+        for (int i = 0; i < 8; ++i) CK(cudaStreamWaitEvent(ctx->aux[i], ctx->ev_begin, 0));
+    }
+    for (int c = 0; c < nchunks; ++c) {
+        const int f0 = c * chunk, nc = std::min(chunk, n - f0);
+        cudaStream_t cs = piped ? ctx->aux[c & 7] : ctx->st;
+#define MARK(name) do { if (!piped) mark(ctx, name); } while (0)
+        if (host_in && !staged_hit) {
+            cudaStream_t hs = piped ? ctx->copy_st : ctx->st;
+            CK(cudaMemcpy2DAsync(b.src + (size_t)f0 * d.src_frame, d.src_pitch, bgr + (size_t)f0 * pitch * src_h, pitch,
+                                 (size_t)src_w * 3, (size_t)src_h * nc, cudaMemcpyHostToDevice, hs));
+            if (piped) {
+                CK(cudaEventRecord(ctx->ev_copy[c], hs));
                 CK(cudaStreamWaitEvent(cs, ctx->ev_copy[c], 0));
             }
-            Dims dc = d;
-            dc.n = nc; dc.f0 = f0; dc.img0 = 3 * f0;
-            Buffers bc = b;
-            const size_t i0 = (size_t)3 * f0;
-            bc.planesA += (size_t)f0 * PA_COUNT * ps; bc.planesB += (size_t)f0 * PB_COUNT * ps;
-            bc.gray += (size_t)f0 * N; bc.dx += (size_t)f0 * N * 2;
-            bc.lsdw += i0 * d.sh * d.swp; bc.pix += i0 * d.pixcap; bc.pxy += i0 * d.pixcap; bc.scs += i0 * d.pixcap;
-            bc.fat += i0 * d.pixcap * 40; bc.order += i0 * d.pixcap; bc.reg += i0 * 2 * d.pixcap;
-            bc.usedbits += i0 * (size_t)((d.pixcap + 31) / 32);
-            bc.pixcount += i0; bc.g2max += i0; bc.cand += i0 * d.segcap; bc.candcount += i0;
-            bc.label += i0 * d.pixcap; bc.csize += i0 * d.pixcap; bc.coff += i0 * d.pixcap; bc.corder += i0 * d.pixcap;
-            bc.cpos += i0 * d.pixcap; bc.tasks += i0 * 256; bc.worklist += i0 * 256; bc.taskctr += 4 * c;
-            bc.candrank += i0 * d.segcap;
-            launch_color_canny(dc, ctx->cp, src + (size_t)f0 * d.src_frame, ctx->tma, bc.planesA, bc.gray, cs);
-            launch_hysteresis(dc, ctx->cfg.dilation_kernel_size, bc.planesA, bc.planesB, cs);
-            launch_lsd_pre(dc, bc.planesB, bc, cs);
-            launch_lsd_core(dc, bc, cs);
-            if (stages & LSF_STAGE_DESCRIBE) launch_gray_sobel(dc, bc.gray, bc.dx, nullptr, cs);
+            MARK("h2d");
+        }
+        Dims dc = d;
+        dc.n = nc; dc.f0 = f0;
+        Buffers bc = b;
+        const size_t i0 = (size_t)3 * f0;
+        bc.planesA += (size_t)f0 * PA_COUNT * ps; bc.planesB += (size_t)f0 * PB_COUNT * ps;
+        bc.gray += (size_t)f0 * N;
+        bc.lsdw += i0 * d.sh * d.swp; bc.pix += i0 * d.pixcap; bc.pxy += i0 * d.pixcap; bc.scs += i0 * d.pixcap;
+        bc.fat += i0 * d.pixcap * 40; bc.order += i0 * d.pixcap; bc.reg += i0 * 2 * d.pixcap;
+        bc.usedbits += i0 * (size_t)((d.pixcap + 31) / 32);
+        bc.pixcount += i0; bc.g2max += i0; bc.cand += i0 * d.segcap; bc.candcount += i0;
+        bc.label += i0 * d.pixcap; bc.csize += i0 * d.pixcap; bc.coff += i0 * d.pixcap; bc.corder += i0 * d.pixcap;
+        bc.cpos += i0 * d.pixcap; bc.tasks += i0 * 256; bc.worklist += i0 * 256; bc.taskctr += 4 * c;
+        bc.candrank += i0 * d.segcap; bc.candlist += i0 * d.segcap; bc.candseg += i0 * d.segcap; bc.candok += i0 * d.segcap;
+        bc.rawseg += i0 * d.segcap; bc.segcount += i0; bc.imgoff += i0; bc.frame_off += f0;
+        launch_color_canny(dc, ctx->cp, src + (size_t)f0 * d.src_frame, ctx->tma, bc.planesA, bc.gray, cs);
+        MARK("color_canny");
+        launch_hysteresis(dc, ctx->cfg.dilation_kernel_size, bc.planesA, bc.planesB, cs);
+        MARK("hysteresis_dilate");
+        launch_lsd_pre(dc, bc.planesB, bc, cs);
+        MARK("lsd_pre");
+        launch_lsd_core(dc, bc, cs);
+        MARK("lsd_grow");
+        if (describe) {
+            launch_gray_sobel(dc, bc.gray, b.dx + (size_t)f0 * N * 2, nullptr, cs);
+            MARK("gray_sobel");
+        }
+        launch_lsd_validate(dc, bc, cs);
+        MARK("lsd_validate");
+        if (piped && c > 0) CK(cudaStreamWaitEvent(cs, ctx->ev_off[c - 1], 0));   // this chunk's first output row
+        launch_seg_offsets(dc, bc, cs);
+        if (piped) CK(cudaEventRecord(ctx->ev_off[c], cs));
+        launch_segments(dc, ctx->cam, bc, (stages & LSF_STAGE_GROUND) ? 1 : 0, cs);
+        MARK("segments");
+        if (describe) {
+            launch_lbd(d, b.o_lines, b.o_frame, b.outcap, b.frame_off + f0, b.frame_off + f0 + nc, b.dx, nullptr, b.o_desc, cs);
+            if (piped) CK(cudaEventRecord(ctx->ev_lbd[c], cs));
+            MARK("lbd");
+        }
+        if (match_prev) {
+            if (piped && c > 0) CK(cudaStreamWaitEvent(cs, ctx->ev_lbd[c - 1], 0));   // descriptors of frame f0 - 1
+            launch_knn_prev(b.o_desc, b.frame_off, f0, nc, k, 256, ctx->carry, ctx->carry_n, b.o_midx, b.o_mdist, cs);
+            MARK("knn_prev");
+        }
+        if (piped) {
             CK(cudaEventRecord(ctx->ev_done[c], cs));
             CK(cudaStreamWaitEvent(ctx->st, ctx->ev_done[c], 0));
         }
-        mark(ctx, "chunks(h2d+color_canny+hysteresis+lsd_pre+lsd_grow+gray_sobel)");
+#undef MARK
     }
-    launch_lsd_validate(d, b, ctx->st);
-    mark(ctx, "lsd_validate");
-    launch_segments(d, ctx->cam, b, (stages & LSF_STAGE_GROUND) ? 1 : 0, ctx->st);
-    mark(ctx, "segments");
-    if (stages & LSF_STAGE_DESCRIBE) {
-        launch_lbd(d, b.o_lines, b.o_frame, b.outcap, b.frame_off + n, b.dx, nullptr, b.o_desc, ctx->st);
-        mark(ctx, "lbd");
-    }
+    if (piped) mark(ctx, "chunks(h2d .. knn_prev)");
     // small results first: counts, offsets, flags
     int *hs = ctx->h_small;
     CK(cudaMemcpyAsync(hs, b.segcount, (size_t)n * 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
@@ -505,16 +575,9 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
         launch_knn(b.o_desc, S, nullptr, ctx->map, ctx->map_n, k, 256, b.o_midx, b.o_mdist, ctx->knn_scratch, ctx->knn_scratch_cap, ctx->st);
         mark(ctx, "knn");
     }
-    if ((stages & LSF_STAGE_MATCH_PREV) && S > 0) {
-        if (!b.o_midx) { CK(dalloc(&b.o_midx, (size_t)b.outcap * 8)); CK(dalloc(&b.o_mdist, (size_t)b.outcap * 8)); }
-        if (!ctx->carry) { ctx->carry_cap = 3 * ctx->segcap; CK(cudaMalloc((void **)&ctx->carry, (size_t)ctx->carry_cap * 32)); }
-        launch_knn_prev(b.o_desc, b.frame_off, n, k, 256, ctx->carry, ctx->carry_n, b.o_midx, b.o_mdist, ctx->st);
-        mark(ctx, "knn_prev");
-    }
     if (stages & LSF_STAGE_MATCH_PREV) {
         // keep the last frame's descriptors for the next batch
         int l0 = hs[n * 3 + n - 1], l1 = hs[n * 3 + n];
-        if (!ctx->carry) { ctx->carry_cap = 3 * ctx->segcap; CK(cudaMalloc((void **)&ctx->carry, (size_t)ctx->carry_cap * 32)); }
         ctx->carry_n = l1 - l0;
         if (ctx->carry_n > 0) CK(cudaMemcpyAsync(ctx->carry, b.o_desc + (size_t)l0 * 32, (size_t)ctx->carry_n * 32, cudaMemcpyDeviceToDevice, ctx->st));
     }
@@ -594,7 +657,7 @@ extern "C" int lsf_describe_batch(lsf_ctx *ctx, lsf_segments *segs)
     fos[S] = S;
     CK(cudaMemcpyAsync(ctx->seg_in + off_frame, fos.data(), (size_t)(S + 1) * 4, cudaMemcpyHostToDevice, ctx->st));
     launch_gray_sobel(ctx->d, ctx->b.gray, ctx->b.dx, nullptr, ctx->st);
-    launch_lbd(ctx->d, (const float *)ctx->seg_in, (const int *)(ctx->seg_in + off_frame), S, (const int *)(ctx->seg_in + off_n),
+    launch_lbd(ctx->d, (const float *)ctx->seg_in, (const int *)(ctx->seg_in + off_frame), S, nullptr, (const int *)(ctx->seg_in + off_n),
                ctx->b.dx, nullptr, ctx->seg_in + off_desc, ctx->st);
     CK(cudaMemcpyAsync(segs->desc, ctx->seg_in + off_desc, (size_t)S * 32, out_kind(segs->mem), ctx->st));
     CK(cudaStreamSynchronize(ctx->st));

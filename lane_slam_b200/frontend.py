@@ -210,6 +210,15 @@ class FrontEnd:
             arrays = a
         return SegmentBatch(n, S, arrays, kk)
 
+    def prefetch(self, frames):
+        """Streaming replay: start copying the NEXT batch of host frames (numpy uint8 [n,H,W,3], ideally pinned) to the
+        device now; a later process() call with the same array consumes the staged copy (lsf_prefetch_batch)."""
+        if not isinstance(frames, np.ndarray) or frames.dtype != np.uint8 or frames.ndim != 4 or frames.shape[3] != 3 \
+                or not frames.flags.c_contiguous:
+            raise ValueError("prefetch expects a C-contiguous uint8 [n,H,W,3] numpy array")
+        n, H, W, _ = frames.shape
+        self._check(self._lib.lsf_prefetch_batch(self._ctx, frames.ctypes.data, n, H, W, W * 3))
+
     # -- pieces of the path on their own -----------------------------------------------------------------------
     def set_color_transform(self, scale, shift):
         """AntiInstagramTransform update (line_detector_node.py:112-114); takes effect at the next batch."""
