@@ -59,10 +59,80 @@ __global__ void __launch_bounds__(256) k_gray_sobel(Dims d, const u8 *__restrict
     }
 }
 
+// ---- fast path (w % 4 == 0): no shared memory, no barriers -----------------------------------------------------
+// A thread owns 4 adjacent columns and marches down GS_R output rows with everything in registers: per input row
+// it loads three aligned words (columns x-4 .. x+7, reflect-101 applied to the loaded words at the frame edges),
+// forms the six horizontal 5-tap sums it needs (columns x-1 .. x+4), keeps the last five rows of those for the
+// vertical 5-tap (-> blurred bytes) and the last three blurred rows for the 3x3 Sobel; one 16-byte store per row.
+// The gray image extended by reflect-101 is symmetric about the border rows / columns and the Gaussian kernel is
+// symmetric, so blurring the extended image reproduces the reflect-101 border of the blurred image that Sobel
+// wants (blurred[-1] == blurred[1]) without a special case.
+constexpr int GS_R = 24;
+
+__device__ __forceinline__ int refl101i(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i); }
+
+__global__ void __launch_bounds__(128) k_gray_sobel4(Dims d, const u8 *__restrict__ gray, short2 *__restrict__ dxy)
+{
+    const int x = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int y0 = (blockIdx.y * 4 + threadIdx.y) * GS_R;
+    const int f = blockIdx.z, w = d.w, h = d.h;
+    if (x >= w || y0 >= h) return;
+    const u8 *src = gray + (size_t)f * h * w;
+    short2 *dst = dxy + (size_t)f * h * w;
+    int hz[5][6];      // horizontal sums of the last five input rows, columns x-1 .. x+4
+    int bl[3][6];      // blurred values of the last three blurred rows, columns x-1 .. x+4
+#pragma unroll
+    for (int t = 0; t < GS_R + 6; ++t) {
+        // input row of this step; blurred row t-4 <-> image row y0 - 3 + (t - 2) ... see below
+        const int gy = refl101i(y0 - 3 + t, h);
+        const u32 *rp = reinterpret_cast<const u32 *>(src + (size_t)gy * w + x);
+        u32 w1 = rp[0];
+        u32 w0 = x > 0 ? rp[-1] : 0u, w2 = x + 4 < w ? rp[1] : 0u;
+        if (x == 0) w0 = __byte_perm(w1, w2, 0x1234);           // columns 4,3,2,1
+        if (x + 4 >= w) w2 = __byte_perm(w0, w1, 0x3456);       // columns w-2, w-3, w-4, w-5
+        // bytes c[0..11] = columns x-4 .. x+7; sum k needs c[k+1 .. k+5]
+        int c[12];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { c[k] = (w0 >> (8 * k)) & 255; c[4 + k] = (w1 >> (8 * k)) & 255; c[8 + k] = (w2 >> (8 * k)) & 255; }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) hz[t % 5][k] = 14 * (c[k + 1] + c[k + 5]) + 62 * (c[k + 2] + c[k + 4]) + 104 * c[k + 3];
+        if (t >= 4) {
+            // blurred row centred on the input row of step t-2, i.e. image row y0 - 1 + (t - 4)
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                int acc = 14 * (hz[(t - 4) % 5][k] + hz[t % 5][k]) + 62 * (hz[(t - 3) % 5][k] + hz[(t - 1) % 5][k]) + 104 * hz[(t - 2) % 5][k];
+                bl[(t - 4) % 3][k] = (acc + 32768) >> 16;
+            }
+        }
+        if (t >= 6) {
+            const int y = y0 + (t - 6);            // output row: blurred rows y-1, y, y+1 = steps t-2, t-1, t
+            if (y < h) {
+                const int *a = bl[(t - 6) % 3], *m = bl[(t - 5) % 3], *b = bl[(t - 4) % 3];
+                int col[6], dif[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { col[k] = a[k] + 2 * m[k] + b[k]; dif[k] = b[k] - a[k]; }
+                uint4 o;
+                u32 *op = &o.x;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    int dx = col[k + 2] - col[k], dy = dif[k] + 2 * dif[k + 1] + dif[k + 2];
+                    op[k] = ((u32)dx & 0xffffu) | ((u32)dy << 16);
+                }
+                *reinterpret_cast<uint4 *>(dst + (size_t)y * w + x) = o;
+            }
+        }
+    }
+}
+
 void launch_gray_sobel(const Dims &d, const u8 *gray, short *dx, short *, cudaStream_t st)
 {
-    dim3 grid((d.w + GT_W - 1) / GT_W, (d.h + GT_H - 1) / GT_H, d.n);
-    k_gray_sobel<<<grid, 256, 0, st>>>(d, gray, reinterpret_cast<short2 *>(dx));
+    if ((d.w & 3) == 0 && d.w >= 8 && d.h >= 8) {
+        dim3 grid((d.w + 127) / 128, (d.h + 4 * GS_R - 1) / (4 * GS_R), d.n), block(32, 4);
+        k_gray_sobel4<<<grid, block, 0, st>>>(d, gray, reinterpret_cast<short2 *>(dx));
+    } else {
+        dim3 grid((d.w + GT_W - 1) / GT_W, (d.h + GT_H - 1) / GT_H, d.n);
+        k_gray_sobel<<<grid, 256, 0, st>>>(d, gray, reinterpret_cast<short2 *>(dx));
+    }
     ++g_launches;
 }
 

@@ -17,7 +17,8 @@ namespace lsf {
 
 constexpr int PT = 256;   // threads
 constexpr int NW = PT / 32;
-constexpr int BR = 8;     // scaled rows per band
+constexpr int BR = 8;     // scaled rows per band (power of two: task decoding uses shifts)
+static_assert(BR == 8, "task decoding below assumes BR == 8");
 constexpr int HZR = 16;   // horizontal-blur rows held per band (source rows s0-2 .. s0+13)
 constexpr int GR = 12;    // blurred rows per band (source rows s0 .. s0+11)
 
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(PT) k_lsd_pre(Dims d, u32 g2_min, const u32 *_
 
         // ---- horizontal blur on bits (taps 4,56,136,56,4; reflect-101), value/255 in Q8 ----
         for (int t = warp; t < HZR * nG; t += NW) {
-            int r = t / nG, xw = listG[t - r * nG], x = xw * 32 + lane;
+            int r = t & (HZR - 1), xw = listG[t >> 4], x = xw * 32 + lane;   // HZR == 16
             const u32 *row = sbits + r * wp;
             int acc = 0;
             if (xw > 0 && xw * 32 + 33 < w) {
@@ -149,14 +150,19 @@ __global__ void __launch_bounds__(PT) k_lsd_pre(Dims d, u32 g2_min, const u32 *_
         __syncthreads();
         // ---- vertical blur -> g (u8) for source rows s0 .. s0+GR-1 (clamped to h-1) ----
         for (int t = warp; t < GR * nG; t += NW) {
-            int r = t / nG, x = listG[t - r * nG] * 32 + lane;
+            int q = t / GR, r = t - q * GR, x = listG[q] * 32 + lane;       // GR is a compile-time constant
             if (x < w) {
                 int gy = min(s0 + r, h - 1);
                 int acc = 0;
+                if (gy >= 2 && gy + 2 < h) {
+                    const u16 *hp = hz + (gy - hz_lo) * w + x;
+                    acc = 4 * ((int)hp[-2 * w] + (int)hp[2 * w]) + 56 * ((int)hp[-w] + (int)hp[w]) + 136 * (int)hp[0];
+                } else {
 #pragma unroll
-                for (int j = -2; j <= 2; ++j) {
-                    int yy = refl101(gy + j, h);
-                    acc += tapw(j) * (int)hz[(yy - hz_lo) * w + x];
+                    for (int j = -2; j <= 2; ++j) {
+                        int yy = refl101(gy + j, h);
+                        acc += tapw(j) * (int)hz[(yy - hz_lo) * w + x];
+                    }
                 }
                 g[r * w + x] = (u8)((acc * 255 + 32768) >> 16);
             }
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(PT) k_lsd_pre(Dims d, u32 g2_min, const u32 *_
         __syncthreads();
         // ---- 0.8x bilinear (INTER_LINEAR_EXACT) -> scaled rows ys0 .. ys0+BR ----
         for (int t = warp; t < (BR + 1) * nS; t += NW) {
-            int rs = t / nS, xs = listS[t - rs * nS] * 32 + lane, ys = ys0 + rs;
+            int q = t / (BR + 1), rs = t - q * (BR + 1), xs = listS[q] * 32 + lane, ys = ys0 + rs;
             if (xs < sw) {
                 u8 val = 0;
                 if (ys < sh) {
@@ -181,8 +187,9 @@ __global__ void __launch_bounds__(PT) k_lsd_pre(Dims d, u32 g2_min, const u32 *_
         }
         __syncthreads();
         // ---- gradient / defined bits on the active words ----
-        for (int t = warp; t < band_rows * nD; t += NW) {
-            int rs = t / nD, xw = listD[t - rs * nD], xs = xw * 32 + lane, ys = ys0 + rs;
+        for (int t = warp; t < BR * nD; t += NW) {
+            int rs = t & (BR - 1), xw = listD[t >> 3], xs = xw * 32 + lane, ys = ys0 + rs;   // BR == 8
+            if (rs >= band_rows) continue;                                                   // warp-uniform
             bool def = false;
             if (xs < sw - 1 && ys < sh - 1) {
                 const u8 *r0 = sc + rs * sw + xs, *r1 = r0 + sw;
@@ -220,8 +227,9 @@ __global__ void __launch_bounds__(PT) k_lsd_pre(Dims d, u32 g2_min, const u32 *_
         __syncthreads();
         // ---- words of the band, then the compact records of the active words ----
         for (int i = tid; i < ntask; i += PT) ow[(size_t)ys0 * swp + i] = LsdWord{wbits[i], wbase[i]};
-        for (int t = warp; t < band_rows * nD; t += NW) {
-            int rs = t / nD, xw = listD[t - rs * nD], xs = xw * 32 + lane, ys = ys0 + rs;
+        for (int t = warp; t < BR * nD; t += NW) {
+            int rs = t & (BR - 1), xw = listD[t >> 3], xs = xw * 32 + lane, ys = ys0 + rs;
+            if (rs >= band_rows) continue;
             u32 bits = wbits[rs * swp + xw], base = wbase[rs * swp + xw];
             if ((bits >> lane) & 1u) {
                 u32 idx = base + __popc(bits & ((1u << lane) - 1u));
