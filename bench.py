@@ -146,7 +146,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = min(os.cpu_count() or 1, len(os.sched_getaffinity(0)))
-    sample = max(cores * 4, 64)
+    sample = max(cores * 16, 128)          # about 10 core-seconds of CPU work per step
     vals = []
     for i in range(args.warmup + args.steps):
         fps, total, wall = cpu_baseline(sample, cores)

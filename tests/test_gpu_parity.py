@@ -279,3 +279,78 @@ def test_device_resident_input_and_determinism(mods):
         assert np.array_equal(b.counts, ref[0]) and np.array_equal(b.lines_px, ref[1])
         assert np.array_equal(b.desc, ref[2]) and np.array_equal(b.keep, ref[3])
     fe.close()
+
+
+def _snapshot(b):
+    return dict(counts=b.counts.copy(), lines=b.lines_px.copy(), ground=b.ground.copy(), keep=b.keep.copy(), desc=b.desc.copy(),
+                midx=None if b.match_idx is None else b.match_idx.copy(), mdist=None if b.match_dist is None else b.match_dist.copy())
+
+
+def _same(a, b):
+    return all((a[k] is None and b[k] is None) or np.array_equal(a[k], b[k]) for k in a)
+
+
+def test_chunk_pipeline_and_prefetch_are_invisible(mods):
+    """The chunk pipeline (several streams, per-chunk tails chained by events) and the staged-input path
+    (lsf_prefetch_batch) must give exactly the single-stream result, frame-to-frame matches across chunk borders
+    included; and the whole sequence must agree with the oracle on counts / keep / match indices."""
+    import torch
+    L, cm, rg, synth, cfg = mods
+    n = 40
+    frames = synth.sequence(n, base_seed=500)
+    fe, cam, Hg = _front_end(L, rg, (480, 640), 0, 480, 640, n)
+    st = L.STAGE_DETECT | L.STAGE_GROUND | L.STAGE_DESCRIBE | L.STAGE_MATCH_PREV
+    fe.set_chunk_frames(-1)
+    fe.reset_sequence()
+    ref = _snapshot(fe.process(frames, stages=st, k=2))
+    for chunk in (7, 16, 39):
+        fe.set_chunk_frames(chunk)
+        fe.reset_sequence()
+        assert _same(ref, _snapshot(fe.process(frames, stages=st, k=2))), "host frames, chunk %d" % chunk
+        fe.reset_sequence()
+        assert _same(ref, _snapshot(fe.process(torch.from_numpy(frames).cuda(), stages=st, k=2))), "device frames, chunk %d" % chunk
+    # staged input: two batches prefetched ahead, consumed in order
+    pinned = torch.from_numpy(frames).pin_memory().numpy()
+    fe.set_chunk_frames(8)
+    fe.prefetch(pinned); fe.prefetch(pinned)
+    for _ in range(2):
+        fe.reset_sequence()
+        assert _same(ref, _snapshot(fe.process(pinned, stages=st, k=2))), "staged input"
+    fe.reset_sequence()
+    assert _same(ref, _snapshot(fe.process(frames, stages=st, k=2))), "unstaged call after staged ones"
+    # oracle on a few frames of the sequence (the full per-stage checks run in the other tests)
+    b = fe.process(frames, stages=st, k=2)
+    prev = None
+    for f in range(0, 6):
+        o = cm.front_end_frame(frames[f], cfg, (480, 640), 0, cam, Hg, descriptors=True)
+        g = b.frame(f)
+        assert g["counts"] == o["counts"] and np.array_equal(g["keep"], o["keep"])
+        if prev is not None and len(prev) and len(g["desc"]):
+            oi, od = cm.knn_hamming(g["desc"], prev, 2)
+            s = b.frame_slice(f)
+            assert np.array_equal(b.match_idx[s], oi) and np.array_equal(b.match_dist[s], od)
+        prev = g["desc"].copy()
+    fe.close()
+
+
+def test_marching_color_canny_variant(mods, monkeypatch):
+    """LSF_MARCH=1 selects the register-marching colour+Canny kernel: same bit-planes, same segments."""
+    L, cm, rg, synth, cfg = mods
+    frames = np.stack([synth.frame(s) for s in (3, 4)] + [synth.frame(5, dense=True)])
+    monkeypatch.setenv("LSF_MARCH", "1")
+    st = _check_batch(L, cm, rg, cfg, frames, (480, 640), 0)
+    assert st["exact_frames"] == st["frames"]
+    st = _check_batch(L, cm, rg, cfg, frames, (480, 640), 160)      # top_cutoff with the marching loader
+    assert st["exact_frames"] == st["frames"]
+
+
+def test_many_components_fallback(mods):
+    """More than 256 connected components in one colour image -> that image is searched as a single task."""
+    L, cm, rg, synth, cfg = mods
+    rng = np.random.default_rng(7)
+    img = np.full((480, 640, 3), 60, np.uint8)
+    for _ in range(900):                                   # isolated short white strokes
+        x, y = int(rng.integers(8, 620)), int(rng.integers(8, 470))
+        img[y:y + 3, x:x + 12] = 255
+    st = _check_batch(L, cm, rg, cfg, img[None], (480, 640), 0, describe=False)
+    assert st["exact_frames"] == 1
