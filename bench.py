@@ -203,7 +203,7 @@ def run_gpu(args):
         fe.reset_sequence()
         b = fe.process(frames, stages=stages, k=K_NN)
         if world > 1:
-            ldist.allgather_kept_segments(b, device=torch.device("cuda", local))
+            ldist.allgather_kept_device(fe, frame_base=rank * n, device=torch.device("cuda", local))   # the path's one exchange step
         return b
 
     def barrier():

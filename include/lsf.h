@@ -183,6 +183,12 @@ LSF_API int lsf_map_clear(lsf_ctx *ctx);
 LSF_API int lsf_map_add(lsf_ctx *ctx, const uint8_t *desc, int n, int mem_kind);
 LSF_API int lsf_map_size(lsf_ctx *ctx);
 
+/* Multi-GPU exchange step: pack the segments of the last batch that line_sanity kept into 72-byte
+ * records  { int32 frame_id (+ frame_base), uint8 color, pad[3], double ground[4], uint8 desc[32] }  in a
+ * ctx-owned DEVICE buffer, ready to be all-gathered (NCCL) and appended to every rank's map.  *records stays
+ * valid until the next call on the ctx.  Needs LSF_STAGE_GROUND (and LSF_STAGE_DESCRIBE for the descriptors). */
+LSF_API int lsf_pack_kept_records(lsf_ctx *ctx, int frame_base, void **records, int *n_records);
+
 /* Forget the previous batch's last frame (start of a new sequence for LSF_STAGE_MATCH_PREV). */
 LSF_API int lsf_reset_sequence(lsf_ctx *ctx);
 

@@ -171,6 +171,56 @@ void launch_segments(const Dims &d, const CamParams &cam, Buffers &b, int do_gro
     ++g_launches;
 }
 
+// ---- kept segments -> 72-byte exchange records (single CTA: scan of the keep flags, then scatter) ----
+__global__ void __launch_bounds__(1024) k_pack_kept(int nseg, int frame_base, const u8 *__restrict__ keep, const int *__restrict__ frame,
+                                                   const u8 *__restrict__ color, const double *__restrict__ ground,
+                                                   const u8 *__restrict__ desc, u8 *__restrict__ rec, int *__restrict__ count)
+{
+    __shared__ int wtot[32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nseg; base += 1024) {
+        const int i = base + tid;
+        const int v = (i < nseg && keep[i]) ? 1 : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wtot[warp] = incl;
+        __syncthreads();
+        int woff = 0;
+        for (int k = 0; k < warp; ++k) woff += wtot[k];
+        const int excl = carry + woff + incl - v;
+        if (v) {
+            u8 *r = rec + (size_t)excl * 72;
+            *reinterpret_cast<int *>(r) = frame[i] + frame_base;
+            *reinterpret_cast<u32 *>(r + 4) = (u32)color[i];
+            const double2 *g = reinterpret_cast<const double2 *>(ground) + 2 * (size_t)i;
+            *reinterpret_cast<double2 *>(r + 8) = g[0];
+            *reinterpret_cast<double2 *>(r + 24) = g[1];
+            const uint4 *dq = reinterpret_cast<const uint4 *>(desc) + 2 * (size_t)i;
+            *reinterpret_cast<uint2 *>(r + 40) = make_uint2(dq[0].x, dq[0].y);
+            *reinterpret_cast<uint2 *>(r + 48) = make_uint2(dq[0].z, dq[0].w);
+            *reinterpret_cast<uint2 *>(r + 56) = make_uint2(dq[1].x, dq[1].y);
+            *reinterpret_cast<uint2 *>(r + 64) = make_uint2(dq[1].z, dq[1].w);
+        }
+        __syncthreads();
+        if (tid == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) *count = carry;
+}
+
+void launch_pack_kept(int nseg, int frame_base, const Buffers &b, u8 *rec, int *count, cudaStream_t st)
+{
+    k_pack_kept<<<1, 1024, 0, st>>>(nseg, frame_base, b.o_keep, b.o_frame, b.o_color, b.o_ground, b.o_desc, rec, count);
+    ++g_launches;
+}
+
 // ---- standalone ground projection + sanity over S segments (lsf_project_filter_batch) ----
 __global__ void k_project_filter(CamParams cam, const float *__restrict__ pixn, const u8 *__restrict__ color, int nseg,
                                  double *__restrict__ ground, u8 *__restrict__ keep)

@@ -45,6 +45,8 @@ struct lsf_ctx {
     // TMA
     TmaDesc tma;
     const u8 *tma_src; int tma_n, tma_h, tma_w; size_t tma_pitch;
+    u8 *kept_rec;         // packed exchange records of the last batch (lsf_pack_kept_records)
+    int last_S, last_stages;
     // staged input: two staging buffers; a prefetch (lsf_prefetch_batch) fills one while the other is being processed
     struct Staged { const u8 *host; int n, h, w; size_t pitch; cudaEvent_t ev; bool valid; unsigned long long seq; };
     u8 *stage_buf[2];
@@ -144,6 +146,7 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     ctx->tma.valid = 0; ctx->tma_src = nullptr;
     ctx->n_events = 0;
     ctx->copy_st = nullptr; ctx->ev_begin = nullptr;
+    ctx->kept_rec = nullptr; ctx->last_S = 0; ctx->last_stages = 0;
     ctx->stage_buf[0] = ctx->stage_buf[1] = nullptr; ctx->stage_seq = 0;
     for (int i = 0; i < 2; ++i) { ctx->staged[i].valid = false; ctx->staged[i].ev = nullptr; }
     for (int i = 0; i < 8; ++i) ctx->aux[i] = nullptr;
@@ -246,6 +249,7 @@ extern "C" void lsf_destroy(lsf_ctx *ctx)
                     ctx->knn_scratch, ctx->tap_tmp, ctx->seg_in, ctx->carry};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->stage_buf[1]) cudaFree(ctx->stage_buf[1]);
+    if (ctx->kept_rec) cudaFree(ctx->kept_rec);
     for (int i = 0; i < 2; ++i) if (ctx->staged[i].ev) cudaEventDestroy(ctx->staged[i].ev);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
     for (auto &e : ctx->events) cudaEventDestroy(e.ev);
@@ -564,6 +568,7 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
                                                        " exceed max_segments_per_color = " + std::to_string(ctx->segcap));
     const int S = hs[n * 3 + n];
     out->n_frames = n; out->n_segments = S;
+    ctx->last_S = S; ctx->last_stages = stages;
     if (S > out->capacity) return fail(ctx, LSF_E_CAPACITY, "lsf_segments.capacity too small: need " + std::to_string(S));
 
     // matching against the ctx map (needs S on the host only for the grid size; queries are device resident)
@@ -723,6 +728,24 @@ extern "C" int lsf_knn_hamming(lsf_ctx *ctx, const uint8_t *query, int nq, const
     }
     CK(cudaStreamSynchronize(ctx->st));
     CK(cudaGetLastError());
+    return LSF_OK;
+}
+
+extern "C" int lsf_pack_kept_records(lsf_ctx *ctx, int frame_base, void **records, int *n_records)
+{
+    if (!ctx || !records || !n_records) return LSF_E_ARG;
+    if (!ctx->have_batch || !(ctx->last_stages & LSF_STAGE_GROUND))
+        return fail(ctx, LSF_E_ARG, "lsf_pack_kept_records: the last batch must have run LSF_STAGE_GROUND");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->kept_rec) CK(cudaMalloc((void **)&ctx->kept_rec, (size_t)ctx->b.outcap * 72 + 16));
+    if (!(ctx->last_stages & LSF_STAGE_DESCRIBE)) CK(cudaMemsetAsync(ctx->b.o_desc, 0, (size_t)ctx->last_S * 32, ctx->st));
+    int *cnt = ctx->b.flags + 2;     // flags[2] is free after the batch
+    launch_pack_kept(ctx->last_S, frame_base, ctx->b, ctx->kept_rec, cnt, ctx->st);
+    CK(cudaMemcpyAsync(ctx->h_small, cnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaGetLastError());
+    *records = ctx->kept_rec;
+    *n_records = ctx->h_small[0];
     return LSF_OK;
 }
 

@@ -64,3 +64,33 @@ def allgather_records(rec, device=None):
 def allgather_kept_segments(batch, frame_base=0, device=None):
     """pack + all-gather: every rank ends up with every rank's kept segments (the shared map snapshot)."""
     return allgather_records(pack_kept(batch, frame_base), device=device)
+
+
+class _DeviceBytes(object):
+    """Zero-copy view of a raw device pointer for torch.as_tensor (CUDA array interface v2)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def allgather_kept_device(fe, frame_base=0, device=None):
+    """The exchange step on the device (NCCL): lsf_pack_kept_records builds this rank's 72-byte records in HBM,
+    the counts and then one padded payload are all-gathered.  Returns (records uint8 [total, 72] CUDA tensor in rank
+    order, per-rank counts).  Nothing passes through host memory except the counts."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    ptr, n = fe.pack_kept_device(frame_base)
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, torch.tensor([n], dtype=torch.int64, device=dev))
+    counts = counts.cpu().tolist()
+    mx = max(counts)
+    if mx == 0:
+        return torch.zeros((0, RECORD_BYTES), dtype=torch.uint8, device=dev), counts
+    send = torch.zeros((mx, RECORD_BYTES), dtype=torch.uint8, device=dev)
+    if n:
+        send.view(-1)[:n * RECORD_BYTES].copy_(torch.as_tensor(_DeviceBytes(ptr, n * RECORD_BYTES), device=dev))
+    recv = torch.empty((world, mx, RECORD_BYTES), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(recv.view(-1), send.view(-1))
+    return torch.cat([recv[r, :counts[r]] for r in range(world)]), counts

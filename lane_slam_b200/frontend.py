@@ -263,6 +263,16 @@ class FrontEnd:
         self._check(self._lib.lsf_knn_hamming(self._ctx, q_ptr, nq, m_ptr, nm, int(k), int(max_dist), MEM_DEVICE,
                                               idx_ptr, dist_ptr))
 
+    def pack_kept_device(self, frame_base=0):
+        """Kept segments of the last batch as 72-byte exchange records in a ctx-owned DEVICE buffer -> (ptr, count)."""
+        ptr, cnt = C.c_void_p(), C.c_int()
+        self._check(self._lib.lsf_pack_kept_records(self._ctx, int(frame_base), C.byref(ptr), C.byref(cnt)))
+        return ptr.value, cnt.value
+
+    def map_add_device(self, ptr, n):
+        """Append n 32-byte descriptors that already live on the device."""
+        self._check(self._lib.lsf_map_add(self._ctx, ptr, int(n), MEM_DEVICE))
+
     def reset_sequence(self):
         """Start a new sequence for STAGE_MATCH_PREV (forget the previous batch's last frame)."""
         self._check(self._lib.lsf_reset_sequence(self._ctx))

@@ -354,3 +354,19 @@ def test_many_components_fallback(mods):
         img[y:y + 3, x:x + 12] = 255
     st = _check_batch(L, cm, rg, cfg, img[None], (480, 640), 0, describe=False)
     assert st["exact_frames"] == 1
+
+
+def test_pack_kept_records_device_equals_host_packing(mods):
+    """lsf_pack_kept_records (device, feeds the NCCL all-gather) == dist.pack_kept on the host copies of the batch."""
+    import torch
+    from lane_slam_b200 import dist as ldist
+    L, cm, rg, synth, cfg = mods
+    frames = synth.sequence(6, base_seed=900)
+    fe, cam, Hg = _front_end(L, rg, (480, 640), 0, 480, 640, 6)
+    b = fe.process(frames, stages=L.STAGE_DETECT | L.STAGE_GROUND | L.STAGE_DESCRIBE)
+    host = ldist.pack_kept(b, frame_base=100)
+    ptr, n = fe.pack_kept_device(frame_base=100)
+    assert n == len(host) == int(b.keep.sum()) and n > 0
+    dev = torch.as_tensor(ldist._DeviceBytes(ptr, n * ldist.RECORD_BYTES), device="cuda").cpu().numpy()
+    assert np.array_equal(dev, host.view(np.uint8).reshape(-1))
+    fe.close()
