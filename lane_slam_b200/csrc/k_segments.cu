@@ -200,8 +200,9 @@ __global__ void __launch_bounds__(1024) k_pack_kept(int nseg, int frame_base, co
             *reinterpret_cast<int *>(r) = frame[i] + frame_base;
             *reinterpret_cast<u32 *>(r + 4) = (u32)color[i];
             const double2 *g = reinterpret_cast<const double2 *>(ground) + 2 * (size_t)i;
-            *reinterpret_cast<double2 *>(r + 8) = g[0];
-            *reinterpret_cast<double2 *>(r + 24) = g[1];
+            const double2 g0 = g[0], g1 = g[1];
+            double *rg = reinterpret_cast<double *>(r + 8);          // records are 72 bytes: 8-byte aligned only
+            rg[0] = g0.x; rg[1] = g0.y; rg[2] = g1.x; rg[3] = g1.y;
             const uint4 *dq = reinterpret_cast<const uint4 *>(desc) + 2 * (size_t)i;
             *reinterpret_cast<uint2 *>(r + 40) = make_uint2(dq[0].x, dq[0].y);
             *reinterpret_cast<uint2 *>(r + 48) = make_uint2(dq[0].z, dq[0].w);
