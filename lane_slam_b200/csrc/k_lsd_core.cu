@@ -186,13 +186,14 @@ struct Prof { long long t_total, t_grow, t_wait, t_rect, t_refine; int grows, ro
 #endif
 constexpr int FAT_WORDS = 40;   // [idx x8][angle(deg) x8][cos x8][sin x8][g2 x8], neighbours row-major, centre skipped
 constexpr int RING = 16;        // queue entries whose fat record can be resident at once
+constexpr int SEED_SLOTS = 16;  // seed candidates of a batch of 32 whose fat record is fetched ahead (most are USED already)
 constexpr float kDEG2RADf = (float)kDEG2RAD, k3_2PIf = (float)k3_2PI, k2PIf = (float)k2PI;
 
 struct Seq3 { double v[3][33]; };   // rows padded so that lanes 0..2 read different banks
 
 struct GrowSm {
     __align__(16) u32 ring[RING][FAT_WORDS];      // fat records of queue positions q (slot q % RING)
-    __align__(16) u32 seedrec[32][FAT_WORDS];     // fat records of the current batch of 32 seed candidates
+    __align__(16) u32 seedrec[SEED_SLOTS][FAT_WORDS];   // fat records of the still unused seed candidates of the current batch
     u32 qxy[RING];                                // xy of the queue entries in the ring
     float2 acc_cs[32];                            // cos / sin of the pixels accepted by the current commit, in order
     Seq3 seq;
@@ -696,6 +697,7 @@ __device__ __forceinline__ void setup_img(Img &im, const Dims &d, int img, const
 //   phase 3  block scan over the roots: component slot, offset of its seed list; tasks appended to the work list
 //            (components of >= BIG_COMP pixels from the front, the others from the back: long chains start first)
 //   phase 4  warp 0: stable partition of order[] by component -> corder[] (+ cpos[] = position in order[])
+constexpr int GROW_PER_SM = 16;  // resident growing warps per SM, measured: 12 -> 5.3 ms, 16 -> 4.7 ms, 20 -> 5.8 ms, 28 (72 regs, spills) -> 6.0 ms
 constexpr int MAXC = 256;        // components (tasks) per image; an image with more is searched as one task
 constexpr int BIG_COMP = 768;
 constexpr int SL_MAX = 8192;     // support pixels whose union-find labels fit in shared memory
@@ -934,7 +936,7 @@ __global__ void __launch_bounds__(256) k_lsd_index(Dims d, const LsdWord *__rest
 // seeds may use.  NFA validation does not touch that state, so it is deferred to kernel 2, where every
 // candidate gets its own warp.
 template <bool SB>
-__global__ void __launch_bounds__(32) k_lsd_grow(Dims d, const LsdWord *__restrict__ lsdw, const LsdPix *__restrict__ pix,
+__global__ void __launch_bounds__(32, GROW_PER_SM) k_lsd_grow(Dims d, const LsdWord *__restrict__ lsdw, const LsdPix *__restrict__ pix,
                                                 const u32 *__restrict__ pxy, const float2 *__restrict__ scs, const u32 *__restrict__ fat,
                                                 const u32 *__restrict__ corder_, const u32 *__restrict__ cpos_,
                                                 const uint2 *__restrict__ tasks, const uint2 *__restrict__ worklist, int worklist_cap,
@@ -985,13 +987,17 @@ __global__ void __launch_bounds__(32) k_lsd_grow(Dims d, const LsdWord *__restri
             u32 cxy = 0;
             float2 ccs = make_float2(0.f, 0.f);
             bool want = ci >= 0 && !is_used<SB>(im, (u32)ci);
+            const u32 wmask = __ballot_sync(FULL, want);
+            const int wrank = __popc(wmask & ((1u << lane) - 1u));
             if (want) {
                 tp = *reinterpret_cast<const uint4 *>(&im.pix[ci]);
                 cxy = im.pxy[ci];
                 ccs = seedcs[ci];
-                const u32 *src = im.fat + (size_t)ci * FAT_WORDS;
+                if (wrank < SEED_SLOTS) {
+                    const u32 *src = im.fat + (size_t)ci * FAT_WORDS;
 #pragma unroll
-                for (int q = 0; q < FAT_WORDS / 4; ++q) cp_async16(&sm.seedrec[lane][q * 4], src + q * 4);
+                    for (int q = 0; q < FAT_WORDS / 4; ++q) cp_async16(&sm.seedrec[wrank][q * 4], src + q * 4);
+                }
             }
             const u32 pfmask = __ballot_sync(FULL, want);
             int k = -1;
@@ -1003,6 +1009,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow(Dims d, const LsdWord *__restri
                 k = __ffs(cnd) - 1;
                 const int seed = __shfl_sync(FULL, ci, k);
                 const bool have = (pfmask >> k) & 1u;   // a seed released by an earlier refine was not pre-fetched
+                const int krank = __popc(pfmask & ((1u << k) - 1u));
                 u32 sdeg = __shfl_sync(FULL, tp.x, k), sg2 = __shfl_sync(FULL, tp.w, k), sxy = __shfl_sync(FULL, cxy, k);
                 float sc = __shfl_sync(FULL, ccs.x, k), ss = __shfl_sync(FULL, ccs.y, k);
                 const u32 srank = __shfl_sync(FULL, cpos, k);   // position of the seed in the image's seed order
@@ -1011,7 +1018,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow(Dims d, const LsdWord *__restri
                     float2 t2 = seedcs[seed];
                     sc = t2.x; ss = t2.y;
                 }
-                const u32 *srec = have ? sm.seedrec[k] : nullptr;
+                const u32 *srec = (have && krank < SEED_SLOTS) ? sm.seedrec[krank] : nullptr;
                 double reg_angle;
                 int nreg = grow<SB>(im, sm, pr, seed, __uint_as_float(sdeg), sg2, sxy, sc, ss, srec, prec, reg_angle);
                 if (nreg < min_reg) continue;
@@ -1136,7 +1143,7 @@ void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st)
         cudaFuncSetAttribute(k_lsd_grow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = smem;
     }
-    const int grid = 148 * 20;     // persistent single-warp blocks (register-limited to about 20 per SM)
+    const int grid = 148 * GROW_PER_SM;     // persistent single-warp blocks, GROW_PER_SM resident per SM (register cap)
     long long *prof = nullptr;
     if (d.debug & 2) { cudaMalloc((void **)&prof, (size_t)wl_cap * 12 * sizeof(long long)); cudaMemsetAsync(prof, 0, (size_t)wl_cap * 12 * sizeof(long long), st); }
     if (used_global)

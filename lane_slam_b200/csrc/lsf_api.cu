@@ -171,9 +171,10 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     ctx->sw = (int)lrint(ctx->w * 0.8); ctx->sh = (int)lrint(ctx->h * 0.8);
     ctx->swp = (ctx->sw + 31) / 32;
     const size_t Np = (size_t)ctx->sh * ctx->sw;
-    // default: every scaled pixel may be a support pixel for small batches; a quarter of them for large ones
+    // default: every scaled pixel may be a support pixel for small batches; an eighth of them for large ones (support
+    // pixels are 0.3-3 % of the image on lane frames; the USED bitmap of this size lives in shared memory)
     ctx->pixcap = cfg->max_pixels_per_color > 0 ? cfg->max_pixels_per_color
-                                                : (int)(ctx->max_batch <= 128 ? Np : std::max<size_t>(4096, Np / 4));
+                                                : (int)(ctx->max_batch <= 128 ? Np : std::max<size_t>(4096, Np / 8));
     if ((size_t)ctx->pixcap > Np) ctx->pixcap = (int)Np;
     ctx->segcap = cfg->max_segments_per_color > 0 ? cfg->max_segments_per_color
                                                   : (int)std::max<size_t>(512, (size_t)ctx->h * ctx->w / 256);
