@@ -50,6 +50,7 @@ struct __align__(16) LsdPix {
     u32 g2;         // gx^2 + gy^2 (norm = sqrt(g2/4))
 };
 constexpr u32 LSD_NONE = 0xffffffffu;
+constexpr int LSD_MAXC = 1024;   // growing tasks per colour image (component slot s -> task s % LSD_MAXC)
 
 // parameters handed to kernels by value
 struct ColorParams {
@@ -73,6 +74,7 @@ struct LsdCand { double x1, y1, x2, y2, width, theta, dx, dy; };
 // ---- device buffers of a context ------------------------------------------------------------------
 struct Buffers {
     u8 *src;            // staged input frames (when the caller passes host memory)
+    u8 *ctab;           // HSV tables of the context (build_color_tables)
     u32 *planesA;       // [n][PA_COUNT][h][wp]
     u32 *planesB;       // [n][PB_COUNT][h][wp]
     u8 *gray;           // [n][h][w]
@@ -85,8 +87,8 @@ struct Buffers {
     u32 *order;         // [n*3][pixcap]  seed order (compact indices)
     u32 *label, *csize, *coff;   // [n*3][pixcap] connected components: root label, size (at roots), seed-list cursor (at roots)
     u32 *corder, *cpos; // [n*3][pixcap]  seed order partitioned by component; position of each entry in order[]
-    uint2 *tasks;       // [n*3][256]     {offset into corder, size} of every component with >= min_reg pixels
-    uint2 *worklist;    // [n*3*256]      (image, task) work list of the growing kernel: big tasks from the front, small from the back
+    uint2 *tasks;       // [n*3][LSD_MAXC] {offset into corder, size} of every task (union of components with >= min_reg pixels)
+    uint2 *worklist;    // [n*3*LSD_MAXC] (image, task) work list of the growing kernel: big tasks from the front, small from the back
     int *taskctr;       // [64][4]        per pipeline chunk: big tasks, small tasks, work cursor, candidates
     u32 *candrank;      // [n*3][segcap]  position of the candidate's seed in order[] (restores the acceptance order)
     uint4 *reg;         // [n*3][2*pixcap] region point list {idx, xy, g2, angle bits} + scratch
@@ -112,8 +114,10 @@ struct Buffers {
 // ---- kernel launchers (one per .cu file) ------------------------------------------------------------
 struct TmaDesc { CUtensorMap map; int valid; };
 
-void launch_color_canny(const Dims &d, const ColorParams &cp, const u8 *src, const TmaDesc &tma, u32 *planesA, u8 *gray,
-                        cudaStream_t st);
+constexpr int COLOR_TABLE_BYTES = 2048 + 768;
+void build_color_tables(const ColorParams &cp, u8 *dst);
+void launch_color_canny(const Dims &d, const ColorParams &cp, const u8 *src, const TmaDesc &tma, const u8 *tables, u32 *planesA,
+                        u8 *gray, cudaStream_t st);
 void launch_hysteresis(const Dims &d, int dilate, const u32 *planesA, u32 *planesB, cudaStream_t st);
 void launch_lsd_pre(const Dims &d, const u32 *planesB, Buffers &b, cudaStream_t st);
 void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st);      // seeds + region growing + refine

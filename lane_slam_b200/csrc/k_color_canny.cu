@@ -8,18 +8,18 @@
 //   .../line_detector_lsd.py:40-47  inRange (x4)
 // Arithmetic = OpenCV 4.13 fixed-point models.
 //
-// Tile 128x16 pixels + halo, staged into shared memory by one TMA 3-D box load of uint32 elements
-// ([frame][row][word], 104 words x 20 rows, zero fill outside the frame) when there is no resize; a gather
+// Tile 128x32 pixels + halo, staged into shared memory by one TMA 3-D box load of uint32 elements
+// ([frame][row][word], 104 words x 36 rows, zero fill outside the frame) when there is no resize; a gather
 // loader otherwise.  Each thread handles runs of 4 pixels with 32-bit shared-memory loads.
 #include "common.cuh"
 
 namespace lsf {
 
-constexpr int TW = 128, TH = 16, HALO = 2;
+constexpr int TW = 128, TH = 32, HALO = 2;
 constexpr int XOFF = 16;                 // bytes of left padding: TMA needs a 16-byte aligned inner start (measured)
 constexpr int ROWB = 416;                // bytes per tile row = 104 uint32: columns -5 .. 132 of the tile
 constexpr int ROWW = ROWB / 4;
-constexpr int BOX_Y = TH + 2 * HALO;     // 20
+constexpr int BOX_Y = TH + 2 * HALO;     // 36
 constexpr int NRUN = TW / 4 + 2;         // 34 runs of 4 columns covering tile columns -4 .. 131
 constexpr int MAGW = 4 * NRUN;           // 136 u16 per magnitude row; column c lives at c + 4
 constexpr int NT = 256;
@@ -47,10 +47,32 @@ __device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_gene
 // byte k (0..19) of a 5-word window
 #define WB(W, k) (int)(((W)[(k) >> 2] >> (8 * ((k) & 3))) & 0xffu)
 
+// HSV tables of a context, built once on the host: [sdiv 256 x i32][hdiv 256 x i32][lutH 256][lutS 256][lutV 256]
+// (lut bit i: value inside colour range i = white, yellow, red1, red2)
+void build_color_tables(const ColorParams &cp, u8 *dst /* COLOR_TABLE_BYTES */)
+{
+    int *sdiv = reinterpret_cast<int *>(dst), *hdiv = sdiv + 256;
+    u8 *lh = dst + 2048, *ls = lh + 256, *lv = ls + 256;
+    sdiv[0] = hdiv[0] = 0;
+    for (int i = 1; i < 256; ++i) {
+        sdiv[i] = (int)lrint((255 << 12) / (1.0 * i));
+        hdiv[i] = (int)lrint((180 << 12) / (6.0 * i));
+    }
+    for (int v = 0; v < 256; ++v) {
+        int mh = 0, ms = 0, mv = 0;
+        for (int i = 0; i < 4; ++i) {
+            mh |= (v >= cp.lo[i][0] && v <= cp.hi[i][0]) << i;
+            ms |= (v >= cp.lo[i][1] && v <= cp.hi[i][1]) << i;
+            mv |= (v >= cp.lo[i][2] && v <= cp.hi[i][2]) << i;
+        }
+        lh[v] = (u8)mh; ls[v] = (u8)ms; lv[v] = (u8)mv;
+    }
+}
+
 template <bool USE_TMA>
 __global__ void __launch_bounds__(NT) k_color_canny(const __grid_constant__ CUtensorMap tmap, Dims d, ColorParams cp,
-                                                    const u8 *__restrict__ src, u32 *__restrict__ planesA,
-                                                    u8 *__restrict__ gray)
+                                                    const u8 *__restrict__ src, const u8 *__restrict__ tables,
+                                                    u32 *__restrict__ planesA, u8 *__restrict__ gray)
 {
     __shared__ __align__(128) u8 tile[BOX_Y * ROWB];
     __shared__ __align__(16) u16 mag[(TH + 2) * MAGW];
@@ -62,16 +84,10 @@ __global__ void __launch_bounds__(NT) k_color_canny(const __grid_constant__ CUte
     const int tid = threadIdx.x;
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH, f = blockIdx.z;
     {
-        s_sdiv[tid] = c_sdiv[tid];
-        s_hdiv[tid] = c_hdiv[tid];
-        int mh = 0, ms = 0, mv = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            mh |= (tid >= cp.lo[i][0] && tid <= cp.hi[i][0]) << i;
-            ms |= (tid >= cp.lo[i][1] && tid <= cp.hi[i][1]) << i;
-            mv |= (tid >= cp.lo[i][2] && tid <= cp.hi[i][2]) << i;
-        }
-        s_lutH[tid] = (u8)mh; s_lutS[tid] = (u8)ms; s_lutV[tid] = (u8)mv;
+        const int *ti = reinterpret_cast<const int *>(tables);
+        s_sdiv[tid] = ti[tid];
+        s_hdiv[tid] = ti[256 + tid];
+        s_lutH[tid] = tables[2048 + tid]; s_lutS[tid] = tables[2304 + tid]; s_lutV[tid] = tables[2560 + tid];
     }
 
     if (USE_TMA) {
@@ -132,14 +148,22 @@ __global__ void __launch_bounds__(NT) k_color_canny(const __grid_constant__ CUte
         if (iy >= 0 && iy < d.h && ix0 + 3 >= 0 && ix0 < d.w) {
             // BORDER_REPLICATE in y: clamp the neighbour rows to the image
             const int rm = max(iy - 1, 0) - (ty0 - HALO), r0 = iy - (ty0 - HALO), rp = min(iy + 1, d.h - 1) - (ty0 - HALO);
-            if (ix0 >= 1 && ix0 + 4 <= d.w - 1) {
-                // fast path: columns ix0-1 .. ix0+4 all inside the image -> 5 words per row
+            const bool wal = (d.w & 3) == 0;       // runs line up with the image borders
+            if ((ix0 >= 1 && ix0 + 4 <= d.w - 1) || (wal && ix0 >= 0 && ix0 + 4 <= d.w)) {
+                // fast path: 5 words per row hold columns ix0-1 .. ix0+4 (window bytes 1 .. 18).  The first / last run of an
+                // image row gets its outside column (BORDER_REPLICATE) by one byte permute per row.
                 const u32 *w0 = reinterpret_cast<const u32 *>(tile + rm * ROWB) + 3 * q;
                 const u32 *w1 = reinterpret_cast<const u32 *>(tile + r0 * ROWB) + 3 * q;
                 const u32 *w2 = reinterpret_cast<const u32 *>(tile + rp * ROWB) + 3 * q;
                 u32 T[5], M[5], B[5];
 #pragma unroll
                 for (int i = 0; i < 5; ++i) { T[i] = w0[i]; M[i] = w1[i]; B[i] = w2[i]; }
+                if (ix0 == 0) {                    // column -1 := column 0 (bytes 1..3 := bytes 4..6)
+                    T[0] = __byte_perm(T[0], T[1], 0x6540); M[0] = __byte_perm(M[0], M[1], 0x6540); B[0] = __byte_perm(B[0], B[1], 0x6540);
+                }
+                if (ix0 + 4 == d.w) {              // column w := column w-1 (bytes 16..18 := bytes 13..15)
+                    T[4] = __byte_perm(T[3], T[4], 0x7321); M[4] = __byte_perm(M[3], M[4], 0x7321); B[4] = __byte_perm(B[3], B[4], 0x7321);
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) best[i] = -1;
 #pragma unroll
@@ -481,8 +505,8 @@ __global__ void __launch_bounds__(CM_WARPS * 32) k_color_canny_march(Dims d, Col
     }
 }
 
-void launch_color_canny(const Dims &d, const ColorParams &cp, const u8 *src, const TmaDesc &tma, u32 *planesA, u8 *gray,
-                        cudaStream_t st)
+void launch_color_canny(const Dims &d, const ColorParams &cp, const u8 *src, const TmaDesc &tma, const u8 *tables, u32 *planesA,
+                        u8 *gray, cudaStream_t st)
 {
     ensure_tables();
     const bool fast = d.identity_geom && d.identity_color && (d.w & 3) == 0 && d.w >= 8 && d.h >= 4 &&
@@ -495,9 +519,9 @@ void launch_color_canny(const Dims &d, const ColorParams &cp, const u8 *src, con
     }
     dim3 grid((d.w + TW - 1) / TW, (d.h + TH - 1) / TH, d.n);
     if (tma.valid)
-        k_color_canny<true><<<grid, NT, 0, st>>>(tma.map, d, cp, src, planesA, gray);
+        k_color_canny<true><<<grid, NT, 0, st>>>(tma.map, d, cp, src, tables, planesA, gray);
     else
-        k_color_canny<false><<<grid, NT, 0, st>>>(tma.map, d, cp, src, planesA, gray);
+        k_color_canny<false><<<grid, NT, 0, st>>>(tma.map, d, cp, src, tables, planesA, gray);
     ++g_launches;
 }
 

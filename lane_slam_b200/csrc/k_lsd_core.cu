@@ -694,11 +694,12 @@ __device__ __forceinline__ void setup_img(Img &im, const Dims &d, int img, const
 //            (raster order inside a bin) -> order[];  warps 1..7: fat record of every pixel (8 lanes per pixel),
 //            union-find merge with the W / NW / N / NE neighbours, seed cos/sin
 //   phase 2  flatten labels (root = smallest index of the component), component sizes
-//   phase 3  block scan over the roots: component slot, offset of its seed list; tasks appended to the work list
-//            (components of >= BIG_COMP pixels from the front, the others from the back: long chains start first)
-//   phase 4  warp 0: stable partition of order[] by component -> corder[] (+ cpos[] = position in order[])
+//   phase 3  component slots; slot s belongs to task s % MAXC (a task is a union of whole components, so any number of
+//            components is fine); tasks appended to the work list (>= BIG_COMP pixels from the front, the others from
+//            the back: long chains start first)
+//   phase 4  stable partition of order[] by task -> corder[] (+ cpos[] = position in order[])
 constexpr int GROW_PER_SM = 16;  // resident growing warps per SM, measured: 12 -> 5.3 ms, 16 -> 4.7 ms, 20 -> 5.8 ms, 28 (72 regs, spills) -> 6.0 ms
-constexpr int MAXC = 256;        // components (tasks) per image; an image with more is searched as one task
+constexpr int MAXC = LSD_MAXC;   // tasks per image: component slot s goes to task s % MAXC (a task = a union of whole components)
 constexpr int BIG_COMP = 768;
 constexpr int SL_MAX = 8192;     // support pixels whose union-find labels fit in shared memory
 
@@ -843,10 +844,13 @@ __global__ void __launch_bounds__(256) k_lsd_index(Dims d, const LsdWord *__rest
     }
     __syncthreads();
     // ---- phase 2: flatten labels, component sizes; then bin counts of the warp's pixels and their cursors ----
-    for (int i = tid; i < n; i += 256) {
-        u32 r = uf_find(lab, (u32)i);
-        label[i] = r;
-        atomicAdd(&csize[r], 1u);
+    for (int i0 = 0; i0 < n; i0 += 256) {
+        const int i = i0 + tid;
+        u32 r = LSD_NONE - (u32)lane;           // lanes past the end: distinct dummy keys
+        if (i < n) { r = uf_find(lab, (u32)i); label[i] = r; }
+        // consecutive pixels mostly share their root: one atomic per distinct root in the warp
+        const u32 mm = __match_any_sync(FULL, r);
+        if (i < n && lane == __ffs(mm) - 1) atomicAdd(&csize[r], (u32)__popc(mm));
     }
     __syncthreads();
     for (int i = tid; i < 8 * 1024; i += 256) sbuf[i] = 0;
@@ -877,39 +881,57 @@ __global__ void __launch_bounds__(256) k_lsd_index(Dims d, const LsdWord *__rest
             for (int w = 0; w < 8; ++w) { u32 c = cnt[w][4 * tid + q]; cnt[w][4 * tid + q] = run; run += c; }
     }
     __syncthreads();
-    // ---- phase 3: seed order (stable scatter of the warp's pixels); component slots, tasks ----
+    // ---- phase 3: seed order (stable scatter of the warp's pixels); component slots -> tasks ----
     warp_stable_scatter(p_lo, p_hi, cnt[warp],
                         [&](int pos, bool &) { return (u32)(1023 - (int)(sqrt((double)im.pix[pos].g2 / 4.0) * bin_coef)); },
                         [&](int pos, u32 dst) { ord[dst] = (u32)pos; });
-    uint2 *tk = tasks + (size_t)img * MAXC;
+    __syncthreads();
+    u32 *tsize = &cnt[0][0];                     // [MAXC] pixels per task (the bin cursors are dead now)
+    for (int i = tid; i < MAXC; i += 256) tsize[i] = 0;
+    __syncthreads();
     for (int i = tid; i < n; i += 256) {
         if (label[i] == (u32)i) {
             const u32 sz = csize[i];
             if (sz >= (u32)min_reg) {
-                const u32 slot = atomicAdd(&s_ncomp, 1u);   // slots in any order: tasks are independent of each other
-                coff[i] = slot;
-                if (slot < MAXC) tk[slot] = make_uint2(atomicAdd(&s_off, sz), sz);
+                const u32 slot = atomicAdd(&s_ncomp, 1u);   // slots in any order: components are independent of each other
+                coff[i] = slot & (MAXC - 1);                // task of this component
+                atomicAdd(&tsize[slot & (MAXC - 1)], sz);
             }
         }
     }
     __syncthreads();
-    const u32 ncomp = s_ncomp;
-    const bool one_task = ncomp > MAXC;          // too many components: search the image as a whole
-    if (one_task && tid == 0) tk[0] = make_uint2(0u, (u32)n);
-    const u32 ntask = one_task ? 1u : ncomp;
-    for (int i = tid; i < 8 * MAXC; i += 256) cnt[i / MAXC][i % MAXC] = 0;
+    const u32 ntask = min(s_ncomp, (u32)MAXC);
+    uint2 *tk = tasks + (size_t)img * MAXC;
+    {
+        // exclusive scan of the task sizes (thread owns tasks 4*tid .. 4*tid+3) -> first seed of every task
+        u32 v[4], sum = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { v[q] = tsize[4 * tid + q]; sum += v[q]; }
+        u32 incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        u32 run = incl - sum;
+        for (int k = 0; k < warp; ++k) run += s_wsum[k];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (4 * tid + q < (int)ntask) tk[4 * tid + q] = make_uint2(run, v[q]);
+            run += v[q];
+        }
+    }
     __syncthreads();
-    if (tid < ntask) {
-        const bool big = tk[tid].y >= (u32)BIG_COMP;
+    for (int t = tid; t < (int)ntask; t += 256) {
+        const bool big = tk[t].y >= (u32)BIG_COMP;
         const int slot = big ? atomicAdd(&taskctr[0], 1) : worklist_cap - 1 - atomicAdd(&taskctr[1], 1);
-        worklist[slot] = make_uint2((u32)img, (u32)tid);
+        worklist[slot] = make_uint2((u32)img, (u32)t);
     }
-    // ---- phase 4: seed list of every component, in image seed order (stable partition of order[]) ----
-    if (one_task) {
-        for (int i = tid; i < n; i += 256) { corder[i] = ord[i]; cpos[i] = (u32)i; }
-        return;
-    }
-    // label[i] <- component slot of pixel i (LSD_NONE for the dropped small components)
+    for (int i = tid; i < 8 * 1024; i += 256) sbuf[i] = 0;
+    // ---- phase 4: seed list of every task, in image seed order (stable partition of order[]) ----
+    // label[i] <- task of pixel i (LSD_NONE for the dropped small components)
     for (int i = tid; i < n; i += 256) {
         const u32 r = label[i];
         label[i] = csize[r] >= (u32)min_reg ? coff[r] : LSD_NONE;
@@ -920,9 +942,9 @@ __global__ void __launch_bounds__(256) k_lsd_index(Dims d, const LsdWord *__rest
         if (sl != LSD_NONE) atomicAdd(&cnt[warp][sl], 1u);
     }
     __syncthreads();
-    if (tid < (int)ncomp) {
-        u32 run = tk[tid].x;
-        for (int w = 0; w < 8; ++w) { const u32 c = cnt[w][tid]; cnt[w][tid] = run; run += c; }
+    for (int t = tid; t < (int)ntask; t += 256) {
+        u32 run = tk[t].x;
+        for (int w = 0; w < 8; ++w) { const u32 c = cnt[w][t]; cnt[w][t] = run; run += c; }
     }
     __syncthreads();
     warp_stable_scatter(p_lo, p_hi, cnt[warp],

@@ -194,6 +194,12 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     CKC(dalloc(&b.src, n * ctx->max_src_h * ctx->max_src_w * 3));
     ctx->stage_buf[0] = b.src;
     for (int i = 0; i < 2; ++i) CKC(cudaEventCreateWithFlags(&ctx->staged[i].ev, cudaEventDisableTiming));
+    CKC(dalloc(&b.ctab, COLOR_TABLE_BYTES));
+    {
+        u8 tab[COLOR_TABLE_BYTES];
+        build_color_tables(ctx->cp, tab);
+        CKC(cudaMemcpy(b.ctab, tab, COLOR_TABLE_BYTES, cudaMemcpyHostToDevice));
+    }
     CKC(dalloc(&b.planesA, n * PA_COUNT * ps));
     CKC(dalloc(&b.planesB, n * PB_COUNT * ps));
     CKC(dalloc(&b.gray, n * N));
@@ -208,7 +214,7 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     CKC(dalloc(&b.order, n * 3 * ctx->pixcap));
     CKC(dalloc(&b.label, n * 3 * ctx->pixcap)); CKC(dalloc(&b.csize, n * 3 * ctx->pixcap)); CKC(dalloc(&b.coff, n * 3 * ctx->pixcap));
     CKC(dalloc(&b.corder, n * 3 * ctx->pixcap)); CKC(dalloc(&b.cpos, n * 3 * ctx->pixcap));
-    CKC(dalloc(&b.tasks, n * 3 * 256)); CKC(dalloc(&b.worklist, n * 3 * 256)); CKC(dalloc(&b.taskctr, 64 * 4));
+    CKC(dalloc(&b.tasks, n * 3 * LSD_MAXC)); CKC(dalloc(&b.worklist, n * 3 * LSD_MAXC)); CKC(dalloc(&b.taskctr, 64 * 4));
     CKC(dalloc(&b.candrank, n * 3 * ctx->segcap));
     CKC(dalloc(&b.reg, n * 3 * ctx->pixcap * 2));
     CKC(dalloc(&b.pixcount, n * 3));
@@ -244,7 +250,7 @@ extern "C" void lsf_destroy(lsf_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     Buffers &b = ctx->b;
-    void *ptrs[] = {ctx->stage_buf[0], b.planesA, b.planesB, b.gray, b.dx, b.lsdw, b.pix, b.pxy, b.fat, b.scs, b.usedbits, b.order, b.label, b.csize, b.coff, b.corder, b.cpos, b.tasks, b.worklist, b.taskctr, b.candrank, b.reg, b.pixcount,
+    void *ptrs[] = {ctx->stage_buf[0], b.ctab, b.planesA, b.planesB, b.gray, b.dx, b.lsdw, b.pix, b.pxy, b.fat, b.scs, b.usedbits, b.order, b.label, b.csize, b.coff, b.corder, b.cpos, b.tasks, b.worklist, b.taskctr, b.candrank, b.reg, b.pixcount,
                     b.g2max, b.rawseg, b.cand, b.candcount, b.candlist, b.candseg, b.candok, b.segcount, b.frame_off, b.flags, b.o_color, b.o_lines, b.o_normals, b.o_centers,
                     b.o_pixn, b.o_nf32, b.o_ground, b.o_keep, b.o_desc, b.o_frame, b.o_midx, b.o_mdist, ctx->map,
                     ctx->knn_scratch, ctx->tap_tmp, ctx->seg_in, ctx->carry};
@@ -318,7 +324,7 @@ static void make_tma(lsf_ctx *ctx, const u8 *src, int n, int sh, int sw, size_t 
     // uint32 elements: the box may be 104 words (416 bytes) wide; 8-bit elements cap the box at 256 bytes
     cuuint64_t gdim[3] = {(cuuint64_t)sw * 3 / 4, (cuuint64_t)sh, (cuuint64_t)n};
     cuuint64_t gstr[2] = {(cuuint64_t)pitch, (cuuint64_t)pitch * sh};
-    cuuint32_t box[3] = {104, 20, 1};
+    cuuint32_t box[3] = {104, 36, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&ctx->tma.map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)src, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -516,10 +522,10 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
         bc.usedbits += i0 * (size_t)((d.pixcap + 31) / 32);
         bc.pixcount += i0; bc.g2max += i0; bc.cand += i0 * d.segcap; bc.candcount += i0;
         bc.label += i0 * d.pixcap; bc.csize += i0 * d.pixcap; bc.coff += i0 * d.pixcap; bc.corder += i0 * d.pixcap;
-        bc.cpos += i0 * d.pixcap; bc.tasks += i0 * 256; bc.worklist += i0 * 256; bc.taskctr += 4 * c;
+        bc.cpos += i0 * d.pixcap; bc.tasks += i0 * LSD_MAXC; bc.worklist += i0 * LSD_MAXC; bc.taskctr += 4 * c;
         bc.candrank += i0 * d.segcap; bc.candlist += i0 * d.segcap; bc.candseg += i0 * d.segcap; bc.candok += i0 * d.segcap;
         bc.rawseg += i0 * d.segcap; bc.segcount += i0; bc.imgoff += i0; bc.frame_off += f0;
-        launch_color_canny(dc, ctx->cp, src + (size_t)f0 * d.src_frame, ctx->tma, bc.planesA, bc.gray, cs);
+        launch_color_canny(dc, ctx->cp, src + (size_t)f0 * d.src_frame, ctx->tma, b.ctab, bc.planesA, bc.gray, cs);
         MARK("color_canny");
         launch_hysteresis(dc, ctx->cfg.dilation_kernel_size, bc.planesA, bc.planesB, cs);
         MARK("hysteresis_dilate");
