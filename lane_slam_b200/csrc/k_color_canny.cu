@@ -83,13 +83,6 @@ __global__ void __launch_bounds__(NT) k_color_canny(const __grid_constant__ CUte
 
     const int tid = threadIdx.x;
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH, f = blockIdx.z;
-    {
-        const int *ti = reinterpret_cast<const int *>(tables);
-        s_sdiv[tid] = ti[tid];
-        s_hdiv[tid] = ti[256 + tid];
-        s_lutH[tid] = tables[2048 + tid]; s_lutS[tid] = tables[2304 + tid]; s_lutV[tid] = tables[2560 + tid];
-    }
-
     if (USE_TMA) {
         const u32 bar_a = smem_u32(&bar);
         if (tid == 0) {
@@ -106,6 +99,12 @@ __global__ void __launch_bounds__(NT) k_color_canny(const __grid_constant__ CUte
                 ::"r"(smem_u32(tile)), "l"(&tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar_a)
                 : "memory");
         }
+        {   // HSV tables while the tile is in flight
+            const int *ti = reinterpret_cast<const int *>(tables);
+            s_sdiv[tid] = ti[tid];
+            s_hdiv[tid] = ti[256 + tid];
+            s_lutH[tid] = tables[2048 + tid]; s_lutS[tid] = tables[2304 + tid]; s_lutV[tid] = tables[2560 + tid];
+        }
         u32 done = 0;
         while (!done) {
             asm volatile(
@@ -117,6 +116,12 @@ __global__ void __launch_bounds__(NT) k_color_canny(const __grid_constant__ CUte
                 : "memory");
         }
     } else {
+        {
+            const int *ti = reinterpret_cast<const int *>(tables);
+            s_sdiv[tid] = ti[tid];
+            s_hdiv[tid] = ti[256 + tid];
+            s_lutH[tid] = tables[2048 + tid]; s_lutS[tid] = tables[2304 + tid]; s_lutV[tid] = tables[2560 + tid];
+        }
         const u8 *fsrc = src + (size_t)f * d.src_frame;
         for (int i = tid; i < BOX_Y * ROWB; i += NT) {
             int r = i / ROWB, k = i - r * ROWB;

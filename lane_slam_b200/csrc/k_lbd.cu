@@ -162,7 +162,7 @@ static void ensure_lbd_tables()
 
 constexpr int LBD_WARPS = 4;
 
-__global__ void __launch_bounds__(LBD_WARPS * 32) k_lbd(Dims d, const float *__restrict__ lines, const int *__restrict__ frame_of_seg,
+__global__ void __launch_bounds__(LBD_WARPS * 32, 8) k_lbd(Dims d, const float *__restrict__ lines, const int *__restrict__ frame_of_seg,
                                                        int nseg_cap, const int *__restrict__ seg_lo_dev,
                                                        const int *__restrict__ seg_hi_dev,
                                                        const short2 *__restrict__ dxy, u8 *__restrict__ desc)
@@ -205,7 +205,29 @@ __global__ void __launch_bounds__(LBD_WARPS * 32) k_lbd(Dims d, const float *__r
                 for (int t = 0; t < hID; ++t) { ox = __fsub_rn(ox, dL1); oy = __fadd_rn(oy, dL0); }
                 float sx = ox, sy = oy;
                 float pL = 0, nL = 0, pO = 0, nO = 0;
-                for (int wID = 0; wID < len; ++wID) {
+                // four gathers in flight per lane; the float sums are still added in walking order
+                int wID = 0;
+                for (; wID + 4 <= len; wID += 4) {
+                    short2 gq[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        int tx = (int)(short)__float2int_rn(roundf(sx));
+                        int ty = (int)(short)__float2int_rn(roundf(sy));
+                        int xc = tx < 0 ? 0 : (tx > W - 1 ? W - 1 : tx);
+                        int yc = ty < 0 ? 0 : (ty > H - 1 ? H - 1 : ty);
+                        gq[u] = img[(size_t)yc * W + xc];
+                        sx = __fadd_rn(sx, dL0);
+                        sy = __fadd_rn(sy, dL1);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float gDL = __fadd_rn(__fmul_rn((float)gq[u].x, dL0), __fmul_rn((float)gq[u].y, dL1));
+                        float gDO = __fadd_rn(__fmul_rn((float)gq[u].x, dO0), __fmul_rn((float)gq[u].y, dO1));
+                        if (gDL > 0) pL = __fadd_rn(pL, gDL); else nL = __fsub_rn(nL, gDL);
+                        if (gDO > 0) pO = __fadd_rn(pO, gDO); else nO = __fsub_rn(nO, gDO);
+                    }
+                }
+                for (; wID < len; ++wID) {
                     int tx = (int)(short)__float2int_rn(roundf(sx));
                     int ty = (int)(short)__float2int_rn(roundf(sy));
                     int xc = tx < 0 ? 0 : (tx > W - 1 ? W - 1 : tx);
@@ -293,7 +315,7 @@ void launch_lbd(const Dims &d, const float *lines, const int *frame_of_seg, int 
                 const int *seg_hi_dev, const short *dx, const short *, u8 *desc, cudaStream_t st)
 {
     ensure_lbd_tables();
-    int grid = 148 * 4;
+    int grid = 148 * 8;
     if (nseg_cap < grid * LBD_WARPS) grid = (nseg_cap + LBD_WARPS - 1) / LBD_WARPS;
     if (grid < 1) grid = 1;
     k_lbd<<<grid, LBD_WARPS * 32, 0, st>>>(d, lines, frame_of_seg, nseg_cap, seg_lo_dev, seg_hi_dev, reinterpret_cast<const short2 *>(dx), desc);
