@@ -80,6 +80,8 @@ struct Buffers {
     u8 *gray;           // [n][h][w]
     short *dx, *dy;     // [n][h][w]  (descriptor path)
     LsdWord *lsdw;      // [n*3][sh][swp]
+    u32 *preact;        // [n*3][ceil(sh/8)][swp] active (image, band, word) tasks of the LSD pre-pass
+    int *prectr;        // [64]           per pipeline chunk: number of active tasks
     LsdPix *pix;        // [n*3][pixcap]
     u32 *pxy;           // [n*3][pixcap]  (y << 16) | x in the scaled image
     float2 *scs;        // [n*3][pixcap]  float(cos), float(sin) of the double angle (sums of a region seeded here)
