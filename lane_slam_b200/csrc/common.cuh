@@ -81,6 +81,7 @@ struct Buffers {
     short *dx, *dy;     // [n][h][w]  (descriptor path)
     LsdWord *lsdw;      // [n*3][sh][swp]
     u32 *preact;        // [n*3][ceil(sh/8)][swp] active (image, band, word) tasks of the LSD pre-pass
+    u32 *prepatch;      // [n*3*ceil(sh/8)*swp][81] scaled 9 x 36 byte patch of every active task (same slot as in preact)
     int *prectr;        // [64]           per pipeline chunk: number of active tasks
     LsdPix *pix;        // [n*3][pixcap]
     u32 *pxy;           // [n*3][pixcap]  (y << 16) | x in the scaled image

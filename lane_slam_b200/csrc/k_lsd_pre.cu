@@ -275,14 +275,16 @@ __global__ void __launch_bounds__(PT) k_lsd_pre(Dims d, u32 g2_min, const u32 *_
 // word, so the work is split in three launches:
 //   k_lsd_pre_a  all tasks: defined bits + count per word; tasks with support pixels are appended to an active list
 //   k_lsd_pre_b  per image: exclusive scan of the word counts (-> LsdWord.base, pixcount)
-//   k_lsd_pre_c  active tasks only: recompute the patch, write the 16-byte records + positions, per-image max gradient
+//   k_lsd_pre_c  active tasks only: from the 324-byte scaled patch pass a kept, write the 16-byte records + positions
+//                and the per-image maximum gradient
 // Arithmetic is op-for-op that of k_lsd_pre (v1, kept for LSF_PRE_V1=1).
 constexpr int PCW = 42;                                    // source columns of a task: 40 xsw .. 40 xsw + 41
+constexpr int PATCH_WORDS = (BR + 1) * 36 / 4;          // the scaled patch of a task: 9 rows x 36 bytes
 struct PreSm {
     unsigned long long win[16];                            // per source row: bit k <-> column 40 xsw - 2 + k (46 bits)
     u16 hz[16][PCW + 2];
     u8 g[12][PCW + 6];
-    u8 sc[BR + 1][36];
+    __align__(4) u8 sc[BR + 1][36];
 };
 
 // fills sm.sc for task (b, xsw); `rows` = the 16 source bit rows s0-2 .. s0+13 of the band ([16][wp], zero outside the
@@ -385,7 +387,7 @@ __device__ __forceinline__ bool pre_load_band(const Dims &d, const u32 *__restri
 }
 
 __global__ void __launch_bounds__(PT) k_lsd_pre_a(Dims d, u32 g2_min, int nbands, const u32 *__restrict__ planesB, LsdWord *__restrict__ lsdw,
-                                                 u32 *__restrict__ active, int *__restrict__ nactive)
+                                                 u32 *__restrict__ active, int *__restrict__ nactive, u32 *__restrict__ patches)
 {
     extern __shared__ __align__(16) u8 pre_dyn[];       // per warp: PreSm + 16 x wp words of source bits
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -426,7 +428,15 @@ __global__ void __launch_bounds__(PT) k_lsd_pre_a(Dims d, u32 g2_min, int nbands
                 }
             }
             if (lane < BR && ys0 + lane < sh) ow[(size_t)(ys0 + lane) * swp + xsw] = LsdWord{mybits, (u32)__popc(mybits)};
-            if (__ballot_sync(0xffffffffu, mybits != 0) && lane == 0) active[atomicAdd(nactive, 1)] = (u32)(t * swp + xsw);
+            if (__ballot_sync(0xffffffffu, mybits != 0)) {
+                // active task: keep its scaled patch (9 x 36 bytes) for the record pass
+                int slot = 0;
+                if (lane == 0) { slot = atomicAdd(nactive, 1); active[slot] = (u32)(t * swp + xsw); }
+                slot = __shfl_sync(0xffffffffu, slot, 0);
+                u32 *dst = patches + (size_t)slot * PATCH_WORDS;
+                const u32 *ps = reinterpret_cast<const u32 *>(&sm.sc[0][0]);
+                for (int i = lane; i < PATCH_WORDS; i += 32) dst[i] = ps[i];
+            }
             __syncwarp();
         }
     }
@@ -469,35 +479,36 @@ __global__ void __launch_bounds__(PT) k_lsd_pre_b(Dims d, LsdWord *__restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(PT) k_lsd_pre_c(Dims d, int nbands, const u32 *__restrict__ planesB, const LsdWord *__restrict__ lsdw,
-                                                 const u32 *__restrict__ active, const int *__restrict__ nactive,
+__global__ void __launch_bounds__(PT) k_lsd_pre_c(Dims d, int nbands, const LsdWord *__restrict__ lsdw, const u32 *__restrict__ active,
+                                                 const int *__restrict__ nactive, const u32 *__restrict__ patches,
                                                  LsdPix *__restrict__ pix, u32 *__restrict__ pxy, u32 *__restrict__ g2max)
 {
-    extern __shared__ __align__(16) u8 pre_dyn[];
+    __shared__ __align__(4) u8 s_sc[NW][BR + 1][36];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t per_warp = sizeof(PreSm) + (size_t)16 * d.wp * 4;
-    PreSm &sm = *reinterpret_cast<PreSm *>(pre_dyn + warp * per_warp);
-    u32 *rows = reinterpret_cast<u32 *>(pre_dyn + warp * per_warp + sizeof(PreSm));
+    u8 (*sc)[36] = s_sc[warp];
     const int swp = d.swp, sh = d.sh;
     const int per_img = nbands * swp, na = *nactive;
     for (int a = blockIdx.x * NW + warp; a < na; a += gridDim.x * NW) {
         const int t = (int)active[a];
         const int img = t / per_img, rem = t - img * per_img, b = rem / swp, xsw = rem - b * swp;
-        const int f = img / 3, c = img - f * 3, ys0 = b * BR;
-        const u32 *src = planesB + ((size_t)f * PB_COUNT + PB_EC0 + c) * (size_t)d.h * d.wp;
+        const int ys0 = b * BR;
         const LsdWord *ow = lsdw + (size_t)img * sh * swp;
         LsdPix *opix = pix + (size_t)img * d.pixcap;
         u32 *opxy = pxy + (size_t)img * d.pixcap;
         __syncwarp();
-        pre_load_band(d, src, b, rows);
-        pre_patch(d, rows, b, xsw, sm);
+        {
+            const u32 *ps = patches + (size_t)a * PATCH_WORDS;
+            u32 *dw = reinterpret_cast<u32 *>(&sc[0][0]);
+            for (int i = lane; i < PATCH_WORDS; i += 32) dw[i] = ps[i];
+        }
+        __syncwarp();
         u32 gmax = 0;
         for (int rs = 0; rs < BR && ys0 + rs < sh; ++rs) {
             const int ys = ys0 + rs, xs = 32 * xsw + lane;
             const LsdWord wd = ow[(size_t)ys * swp + xsw];
             if ((wd.bits >> lane) & 1u) {
                 const u32 idx = wd.base + __popc(wd.bits & ((1u << lane) - 1u));
-                const u8 *r0 = &sm.sc[rs][lane], *r1 = &sm.sc[rs + 1][lane];
+                const u8 *r0 = &sc[rs][lane], *r1 = &sc[rs + 1][lane];
                 const int DA = (int)r1[1] - (int)r0[0], BC = (int)r0[1] - (int)r1[0];
                 const int gx = DA + BC, gy = DA - BC;
                 const u32 g2 = (u32)(gx * gx + gy * gy);
@@ -540,7 +551,8 @@ void launch_lsd_pre(const Dims &d, const u32 *planesB, Buffers &b, cudaStream_t 
     const double rho = 2.0 / sin(3.14159265358979323846 * 22.5 / 180.0);
     u32 g2_min = 0;
     while (!(sqrt((double)g2_min / 4.0) > rho)) ++g2_min;
-    if (getenv("LSF_PRE_V1")) {
+    const size_t smem2 = NW * (sizeof(PreSm) + (size_t)16 * d.wp * 4);
+    if (getenv("LSF_PRE_V1") || smem2 > 200 * 1024) {     // v1: frames wider than ~12 000 pixels (and A/B runs)
         k_lsd_pre<<<d.n * 3, PT, smem, st>>>(d, g2_min, planesB, b.lsdw, b.pix, b.pxy, b.pixcount, b.g2max, b.flags);
         ++g_launches;
         return;
@@ -548,16 +560,14 @@ void launch_lsd_pre(const Dims &d, const u32 *planesB, Buffers &b, cudaStream_t 
     const int nbands = (d.sh + BR - 1) / BR;
     const long long nrow = (long long)d.n * 3 * nbands;
     const int grid_a = (int)std::min<long long>((nrow + NW - 1) / NW, 148 * 8);
-    const size_t smem2 = NW * (sizeof(PreSm) + (size_t)16 * d.wp * 4);
     static size_t attr2 = 0;
     if (smem2 > attr2) {
         cudaFuncSetAttribute(k_lsd_pre_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-        cudaFuncSetAttribute(k_lsd_pre_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
         attr2 = smem2;
     }
-    k_lsd_pre_a<<<grid_a, PT, smem2, st>>>(d, g2_min, nbands, planesB, b.lsdw, b.preact, b.prectr);
+    k_lsd_pre_a<<<grid_a, PT, smem2, st>>>(d, g2_min, nbands, planesB, b.lsdw, b.preact, b.prectr, b.prepatch);
     k_lsd_pre_b<<<d.n * 3, PT, 0, st>>>(d, b.lsdw, b.pixcount, b.g2max, b.flags);
-    k_lsd_pre_c<<<148 * 8, PT, smem2, st>>>(d, nbands, planesB, b.lsdw, b.preact, b.prectr, b.pix, b.pxy, b.g2max);
+    k_lsd_pre_c<<<148 * 8, PT, 0, st>>>(d, nbands, b.lsdw, b.preact, b.prectr, b.prepatch, b.pix, b.pxy, b.g2max);
     g_launches += 3;
 }
 

@@ -207,6 +207,7 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     b.dy = nullptr;
     CKC(dalloc(&b.lsdw, n * 3 * (size_t)ctx->sh * ctx->swp));
     CKC(dalloc(&b.preact, n * 3 * (size_t)((ctx->sh + 7) / 8) * ctx->swp));
+    CKC(dalloc(&b.prepatch, n * 3 * (size_t)((ctx->sh + 7) / 8) * ctx->swp * 81));
     CKC(dalloc(&b.prectr, 64));
     CKC(dalloc(&b.pix, n * 3 * ctx->pixcap));
     CKC(dalloc(&b.pxy, n * 3 * ctx->pixcap));
@@ -252,7 +253,7 @@ extern "C" void lsf_destroy(lsf_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     Buffers &b = ctx->b;
-    void *ptrs[] = {ctx->stage_buf[0], b.ctab, b.planesA, b.planesB, b.gray, b.dx, b.lsdw, b.preact, b.prectr, b.pix, b.pxy, b.fat, b.scs, b.usedbits, b.order, b.label, b.csize, b.coff, b.corder, b.cpos, b.tasks, b.worklist, b.taskctr, b.candrank, b.reg, b.pixcount,
+    void *ptrs[] = {ctx->stage_buf[0], b.ctab, b.planesA, b.planesB, b.gray, b.dx, b.lsdw, b.preact, b.prepatch, b.prectr, b.pix, b.pxy, b.fat, b.scs, b.usedbits, b.order, b.label, b.csize, b.coff, b.corder, b.cpos, b.tasks, b.worklist, b.taskctr, b.candrank, b.reg, b.pixcount,
                     b.g2max, b.rawseg, b.cand, b.candcount, b.candlist, b.candseg, b.candok, b.segcount, b.frame_off, b.flags, b.o_color, b.o_lines, b.o_normals, b.o_centers,
                     b.o_pixn, b.o_nf32, b.o_ground, b.o_keep, b.o_desc, b.o_frame, b.o_midx, b.o_mdist, ctx->map,
                     ctx->knn_scratch, ctx->tap_tmp, ctx->seg_in, ctx->carry};
@@ -521,6 +522,7 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
         bc.planesA += (size_t)f0 * PA_COUNT * ps; bc.planesB += (size_t)f0 * PB_COUNT * ps;
         bc.gray += (size_t)f0 * N;
         bc.preact += i0 * (size_t)((d.sh + 7) / 8) * d.swp; bc.prectr += c;
+        bc.prepatch += i0 * (size_t)((d.sh + 7) / 8) * d.swp * 81;
         bc.lsdw += i0 * d.sh * d.swp; bc.pix += i0 * d.pixcap; bc.pxy += i0 * d.pixcap; bc.scs += i0 * d.pixcap;
         bc.fat += i0 * d.pixcap * 40; bc.order += i0 * d.pixcap; bc.reg += i0 * 2 * d.pixcap;
         bc.usedbits += i0 * (size_t)((d.pixcap + 31) / 32);
