@@ -43,6 +43,16 @@ ALGO_BYTES = {
 }
 
 
+# DRAM traffic per frame (dram__bytes_read.sum + dram__bytes_write.sum) of the dense kernels, from the ncu --set full
+# capture profiles/r01f_ncu_full_296frames.csv (296 frames per launch, divided by 296)
+TRAFFIC_BYTES = {
+    "color_canny": (272.836e6 + 151.673e6) / 296,
+    "hysteresis_dilate": (56.880e6 + 28.300e6) / 296,
+    "lsd_pre": (34.587e6 + 8.536e6 + 42.403e6 + 16.717e6) / 296,
+    "gray_sobel": (92.231e6 + 306.249e6) / 296,
+}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -283,14 +293,17 @@ def run_gpu(args):
         ent = {"kernel": name, "ms_per_step": per, "share": ms / tot_ms}
         if name in ALGO_BYTES:
             gbs = ALGO_BYTES[name] * n / (per * 1e-3) / 1e9
-            ent.update(bound="hbm", algorithmic_bytes_per_frame=ALGO_BYTES[name], achieved_gbs=gbs, frac=gbs / peak)
+            ent.update(bound="hbm", algorithmic_bytes_per_frame=ALGO_BYTES[name], achieved_gbs=gbs, frac=gbs / peak,
+                       dram_traffic_bytes_per_launch=TRAFFIC_BYTES[name] * n)
         else:
             ent.update(bound="latency")
         kernels.append(ent)
     dense = [k for k in kernels if k["bound"] == "hbm"]
     dom = max(dense, key=lambda k: k["ms_per_step"])
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": dom["frac"], "traffic": dom["dram_traffic_bytes_per_launch"],
+                "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_frame"] * n, "peak_source": peak_src,
+                "traffic_source": "ncu --set full, profiles/r01f_ncu_full_296frames.csv, scaled from 296 to %d frames" % n,
                 "note": "dominant HBM-bound kernel; the LSD search (lsd_core) is latency-bound, see 'kernels'"}
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),

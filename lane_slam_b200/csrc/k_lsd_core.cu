@@ -309,6 +309,11 @@ __device__ int grow(const Img &im, GrowSm &sm, Prof &pr, int seed, float seed_de
                 deg = __uint_as_float(rec[8 + j]); c = __uint_as_float(rec[16 + j]); s = __uint_as_float(rec[24 + j]);
                 g2 = rec[32 + j];
                 xy = sm.qxy[slot] + (u32)nd;
+                // a visit that may be accepted: start pulling its fat record towards L2 now (the queue is short, the
+                // cp.async issued at acceptance would otherwise pay the full DRAM latency one round later)
+                const u32 *nf = im.fat + (size_t)ni * FAT_WORDS;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nf));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nf + 32));
             }
         }
         u32 R = __ballot_sync(FULL, idx >= 0);          // undecided visits
