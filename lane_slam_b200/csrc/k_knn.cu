@@ -1,4 +1,4 @@
-// k_knn.cu -- K13: exact brute-force Hamming kNN over packed 256-bit descriptors (__popc).
+// k_knn.cu -- K13: exact brute-force Hamming kNN over packed 256-bit descriptors (carry-save adders + __popc).
 //
 // Replaces BinaryDescriptorMatcher::knnMatch (src/line_descriptor/src/binary_descriptor_matcher.cpp:258-335,
 // Mihasher::query :635-753) and the distance kernel match() (src/line_descriptor/src/bitops_custom.hpp:83-96).
@@ -16,6 +16,24 @@ namespace lsf {
 constexpr int KT = 256;        // threads = queries per CTA
 constexpr int KTILE = 256;     // map descriptors per shared-memory tile (8 KB)
 
+// Hamming distance of two 256-bit codes.  Eight POPC per pair saturate the XU pipe (ncu: 92 % of peak, POPC issues at a
+// quarter of the integer ALU rate), so the eight XOR words first go through a carry-save adder tree (LOP3 xor3 / majority
+// on the ALU pipe) that leaves four words of weight 1, 2, 4, 4: four POPC instead of eight.
+__device__ __forceinline__ u32 xor3(u32 a, u32 b, u32 c) { return a ^ b ^ c; }
+__device__ __forceinline__ u32 maj3(u32 a, u32 b, u32 c) { return (a & b) | (c & (a | b)); }
+__device__ __forceinline__ int hamming256(const uint4 &qa, const uint4 &qb, const uint4 &a, const uint4 &b)
+{
+    const u32 x0 = qa.x ^ a.x, x1 = qa.y ^ a.y, x2 = qa.z ^ a.z, x3 = qa.w ^ a.w;
+    const u32 x4 = qb.x ^ b.x, x5 = qb.y ^ b.y, x6 = qb.z ^ b.z, x7 = qb.w ^ b.w;
+    const u32 s1 = xor3(x0, x1, x2), c1 = maj3(x0, x1, x2);
+    const u32 s2 = xor3(x3, x4, x5), c2 = maj3(x3, x4, x5);
+    const u32 s3 = xor3(s1, s2, x6), c3 = maj3(s1, s2, x6);
+    const u32 ones = s3 ^ x7, c4 = s3 & x7;
+    const u32 t = xor3(c1, c2, c3), f1 = maj3(c1, c2, c3);
+    const u32 twos = t ^ c4, f2 = t & c4;
+    return __popc(ones) + 2 * __popc(twos) + 4 * (__popc(f1) + __popc(f2));
+}
+
 template <int K>
 __device__ __forceinline__ void knn_insert(int (&bd)[K], int (&bi)[K], int dd, int idx)
 {
@@ -28,6 +46,9 @@ __device__ __forceinline__ void knn_insert(int (&bd)[K], int (&bi)[K], int dd, i
     if (bd[0] > dd) { bd[0] = dd; bi[0] = idx; }
 }
 
+constexpr int QPT = 1;         // queries per thread (2 was measured slower: 0.51 vs 0.42 ms at C4, although the one-query
+                               // kernel is MIO-throttled on the tile broadcasts)
+
 template <int K>
 __global__ void __launch_bounds__(KT) k_knn_partial(const uint4 *__restrict__ q, int nq_cap, const int *__restrict__ nq_dev,
                                                    const uint4 *__restrict__ m, int nm, int max_dist, int chunk,
@@ -35,15 +56,20 @@ __global__ void __launch_bounds__(KT) k_knn_partial(const uint4 *__restrict__ q,
 {
     __shared__ uint4 tile[KTILE * 2];
     const int nq = nq_dev ? min(*nq_dev, nq_cap) : nq_cap;
-    const int qi = blockIdx.x * KT + threadIdx.x;
-    if (blockIdx.x * KT >= nq) return;
+    if (blockIdx.x * KT * QPT >= nq) return;
     const int split = blockIdx.y, nsplit = gridDim.y;
     const int m0 = split * chunk, m1 = min(nm, m0 + chunk);
-    uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
-    if (qi < nq) { qa = q[2 * (size_t)qi]; qb = q[2 * (size_t)qi + 1]; }
-    int bd[K], bi[K];
+    int qi[QPT];
+    uint4 qa[QPT], qb[QPT];
+    int bd[QPT][K], bi[QPT][K];
 #pragma unroll
-    for (int j = 0; j < K; ++j) { bd[j] = 0x7fffffff; bi[j] = -1; }
+    for (int u = 0; u < QPT; ++u) {
+        qi[u] = (blockIdx.x * QPT + u) * KT + threadIdx.x;
+        qa[u] = make_uint4(0, 0, 0, 0); qb[u] = qa[u];
+        if (qi[u] < nq) { qa[u] = q[2 * (size_t)qi[u]]; qb[u] = q[2 * (size_t)qi[u] + 1]; }
+#pragma unroll
+        for (int j = 0; j < K; ++j) { bd[u][j] = 0x7fffffff; bi[u][j] = -1; }
+    }
     for (int t0 = m0; t0 < m1; t0 += KTILE) {
         const int nt = min(KTILE, m1 - t0);
         __syncthreads();
@@ -51,16 +77,21 @@ __global__ void __launch_bounds__(KT) k_knn_partial(const uint4 *__restrict__ q,
         __syncthreads();
 #pragma unroll 4
         for (int j = 0; j < nt; ++j) {
-            uint4 a = tile[2 * j], b = tile[2 * j + 1];
-            int dd = __popc(qa.x ^ a.x) + __popc(qa.y ^ a.y) + __popc(qa.z ^ a.z) + __popc(qa.w ^ a.w) +
-                     __popc(qb.x ^ b.x) + __popc(qb.y ^ b.y) + __popc(qb.z ^ b.z) + __popc(qb.w ^ b.w);
-            if (dd < bd[K - 1] && dd <= max_dist) knn_insert<K>(bd, bi, dd, t0 + j);
+            const uint4 a = tile[2 * j], b = tile[2 * j + 1];
+#pragma unroll
+            for (int u = 0; u < QPT; ++u) {
+                const int dd = hamming256(qa[u], qb[u], a, b);
+                if (dd < bd[u][K - 1] && dd <= max_dist) knn_insert<K>(bd[u], bi[u], dd, t0 + j);
+            }
         }
     }
-    if (qi < nq) {
-        size_t o = ((size_t)qi * nsplit + split) * K;
 #pragma unroll
-        for (int j = 0; j < K; ++j) { pidx[o + j] = bi[j]; pdist[o + j] = bd[j]; }
+    for (int u = 0; u < QPT; ++u) {
+        if (qi[u] < nq) {
+            size_t o = ((size_t)qi[u] * nsplit + split) * K;
+#pragma unroll
+            for (int j = 0; j < K; ++j) { pidx[o + j] = bi[u][j]; pdist[o + j] = bd[u][j]; }
+        }
     }
 }
 
@@ -121,8 +152,7 @@ __global__ void __launch_bounds__(128) k_knn_prev(const uint4 *__restrict__ desc
             __syncthreads();
             for (int j = 0; j < m; ++j) {
                 uint4 a = tile[2 * j], b = tile[2 * j + 1];
-                int dd = __popc(qa.x ^ a.x) + __popc(qa.y ^ a.y) + __popc(qa.z ^ a.z) + __popc(qa.w ^ a.w) +
-                         __popc(qbv.x ^ b.x) + __popc(qbv.y ^ b.y) + __popc(qbv.z ^ b.z) + __popc(qbv.w ^ b.w);
+                int dd = hamming256(qa, qbv, a, b);
                 if (dd < bd[K - 1] && dd <= max_dist) knn_insert<K>(bd, bi, dd, t0 + j);
             }
         }
@@ -151,7 +181,7 @@ static int knn_K(int k) { return k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : 8; }
 
 static int knn_nsplit(int nq, int nm)
 {
-    int qtiles = (nq + KT - 1) / KT;
+    int qtiles = (nq + KT * QPT - 1) / (KT * QPT);
     if (qtiles < 1) qtiles = 1;
     int ns = (148 * 4 + qtiles - 1) / qtiles;
     int maxs = (nm + KTILE * 2 - 1) / (KTILE * 2);
@@ -173,7 +203,7 @@ void launch_knn(const u8 *q, int nq_cap, const int *nq_dev, const u8 *m, int nm,
     int chunk = (nm + nsplit - 1) / nsplit;
     chunk = ((chunk + KTILE - 1) / KTILE) * KTILE;
     int *pidx = (int *)scratch, *pdist = pidx + (size_t)nq_cap * nsplit * K;
-    dim3 grid((nq_cap + KT - 1) / KT, nsplit);
+    dim3 grid((nq_cap + KT * QPT - 1) / (KT * QPT), nsplit);
     const uint4 *q4 = (const uint4 *)q, *m4 = (const uint4 *)m;
     switch (K) {
     case 1: k_knn_partial<1><<<grid, KT, 0, st>>>(q4, nq_cap, nq_dev, m4, nm, max_dist, chunk, pidx, pdist); break;
