@@ -207,10 +207,10 @@ __global__ void __launch_bounds__(LBD_WARPS * 32, 8) k_lbd(Dims d, const float *
                 float pL = 0, nL = 0, pO = 0, nO = 0;
                 // four gathers in flight per lane; the float sums are still added in walking order
                 int wID = 0;
-                for (; wID + 4 <= len; wID += 4) {
-                    short2 gq[4];
+                for (; wID + 8 <= len; wID += 8) {
+                    short2 gq[8];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < 8; ++u) {
                         int tx = (int)(short)__float2int_rn(roundf(sx));
                         int ty = (int)(short)__float2int_rn(roundf(sy));
                         int xc = tx < 0 ? 0 : (tx > W - 1 ? W - 1 : tx);
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(LBD_WARPS * 32, 8) k_lbd(Dims d, const float *
                         sy = __fadd_rn(sy, dL1);
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < 8; ++u) {
                         float gDL = __fadd_rn(__fmul_rn((float)gq[u].x, dL0), __fmul_rn((float)gq[u].y, dL1));
                         float gDO = __fadd_rn(__fmul_rn((float)gq[u].x, dO0), __fmul_rn((float)gq[u].y, dO1));
                         if (gDL > 0) pL = __fadd_rn(pL, gDL); else nL = __fsub_rn(nL, gDL);
