@@ -69,8 +69,9 @@ typedef struct lsf_config {
     int32_t max_pixels_per_color;   /* LSD support pixels per frame and colour */
     int32_t device;              /* CUDA device ordinal */
     int32_t chunk_frames;        /* frames per pipeline chunk: a batch is cut into chunks whose host->device copy and
-                                    kernels overlap on several streams.  0 = automatic (about n/8, one chunk below 64
-                                    frames), < 0 = never chunk (one stream; lsf_last_timings then lists every kernel) */
+                                    kernels overlap on several streams.  0 = automatic (n/8 for host frames, n/2 for
+                                    frames already on the device, one chunk below 64 frames), < 0 = never chunk (one
+                                    stream; lsf_last_timings then lists every kernel) */
     int32_t reserved[6];
 } lsf_config;
 

@@ -18,7 +18,6 @@ namespace lsf {
 constexpr int TW = 128, TH = 32, HALO = 2;
 constexpr int XOFF = 16;                 // bytes of left padding: TMA needs a 16-byte aligned inner start (measured)
 constexpr int ROWB = 416;                // bytes per tile row = 104 uint32: columns -5 .. 132 of the tile
-constexpr int ROWW = ROWB / 4;
 constexpr int BOX_Y = TH + 2 * HALO;     // 36
 constexpr int NRUN = TW / 4 + 2;         // 34 runs of 4 columns covering tile columns -4 .. 131
 constexpr int MAGW = 4 * NRUN;           // 136 u16 per magnitude row; column c lives at c + 4
@@ -28,6 +27,7 @@ __constant__ int c_sdiv[256];
 __constant__ int c_hdiv[256];
 static bool g_tabs_ready = false;
 
+// sdiv / hdiv for the marching kernel (the tiled kernel reads the per-context table, build_color_tables)
 static void ensure_tables()
 {
     if (g_tabs_ready) return;

@@ -9,10 +9,12 @@
 // order with the region angle updated after every accepted pixel; later seeds see the USED flags earlier
 // regions left behind), so one warp owns one image and the cost is a chain of dependent steps.  The layout
 // exists to make every step of that chain short:
-//   k_lsd_index  (parallel, 256 threads per image): the seed order (stable counting sort) and one 160-byte
+//   k_lsd_index  (parallel, 256 threads per image): the seed order (stable counting sort), one 160-byte
 //                "fat" record per support pixel holding the compact index, angle, cos/sin and gradient of its
-//                8 neighbours, so that consuming a queue entry needs ONE fetch instead of three dependent ones;
-//   k_lsd_grow   (one warp per image): fat records are pulled into a shared-memory ring with cp.async at the
+//                8 neighbours, so that consuming a queue entry needs ONE fetch instead of three dependent ones,
+//                and the 8-connected components of the support pixels: region growing never leaves a component,
+//                so every component (grouped into at most 1024 tasks per image) is searched independently;
+//   k_lsd_grow   (persistent warps pulling tasks): fat records are pulled into a shared-memory ring with cp.async at the
 //                moment a pixel is accepted (and for upcoming seeds at batch load), USED flags live in a
 //                shared-memory bitmap, four queue entries (32 neighbour visits) are resolved per round, and the
 //                region angle is re-evaluated only when a visit is too close to the tolerance to decide
@@ -769,7 +771,7 @@ __global__ void __launch_bounds__(256) k_lsd_index(Dims d, const LsdWord *__rest
     u32 (*cnt)[1024] = reinterpret_cast<u32 (*)[1024]>(sbuf);
     u32 *s_label = sbuf;
     __shared__ u32 s_wsum[8];
-    __shared__ u32 s_ncomp, s_off;
+    __shared__ u32 s_ncomp;
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     Img im;
     setup_img(im, d, img, lsdw, pix, pxy, nullptr, nullptr, pixcount);
@@ -787,7 +789,7 @@ __global__ void __launch_bounds__(256) k_lsd_index(Dims d, const LsdWord *__rest
     const int p_lo = min(n, warp * seg), p_hi = min(n, p_lo + seg);
     u32 *lab = n <= SL_MAX ? s_label : label;
     for (int i = tid; i < n; i += 256) { lab[i] = (u32)i; csize[i] = 0; }
-    if (tid == 0) { s_ncomp = 0; s_off = 0; }
+    if (tid == 0) s_ncomp = 0;
     __syncthreads();
     // ---- phase 1: fat records + unions; seed cos/sin ----
     for (int i = p_lo + lane; i < p_hi; i += 32) {
