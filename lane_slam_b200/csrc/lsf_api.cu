@@ -372,6 +372,13 @@ extern "C" long long lsf_launch_count(const lsf_ctx *ctx) { return ctx ? g_launc
 extern "C" void *lsf_stream(lsf_ctx *ctx) { return ctx ? (void *)ctx->st : nullptr; }
 extern "C" const char *lsf_version(void) { return "lsf 0.1 (sm_100a)"; }
 
+// host -> device copy of `rows` rows of `row_bytes` bytes: one linear copy when the host rows are contiguous
+static cudaError_t h2d_rows(void *dst, const void *src, size_t src_pitch, size_t row_bytes, size_t rows, cudaStream_t st)
+{
+    if (src_pitch == row_bytes) return cudaMemcpyAsync(dst, src, row_bytes * rows, cudaMemcpyHostToDevice, st);
+    return cudaMemcpy2DAsync(dst, row_bytes, src, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice, st);
+}
+
 extern "C" int lsf_prefetch_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int src_h, int src_w, size_t pitch)
 {
     if (!ctx) return LSF_E_ARG;
@@ -383,8 +390,7 @@ extern "C" int lsf_prefetch_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int s
     // the staging buffer that is not holding an unconsumed batch; the oldest one if both do
     int slot = !ctx->staged[0].valid ? 0 : !ctx->staged[1].valid ? 1 : (ctx->staged[0].seq < ctx->staged[1].seq ? 0 : 1);
     lsf_ctx::Staged &sg = ctx->staged[slot];
-    CK(cudaMemcpy2DAsync(ctx->stage_buf[slot], (size_t)src_w * 3, bgr, pitch, (size_t)src_w * 3, (size_t)src_h * n, cudaMemcpyHostToDevice,
-                         ctx->copy_st));
+    CK(h2d_rows(ctx->stage_buf[slot], bgr, pitch, (size_t)src_w * 3, (size_t)src_h * n, ctx->copy_st));
     CK(cudaEventRecord(sg.ev, ctx->copy_st));
     sg.host = bgr; sg.n = n; sg.h = src_h; sg.w = src_w; sg.pitch = pitch; sg.valid = true; sg.seq = ++ctx->stage_seq;
     return LSF_OK;
@@ -507,8 +513,8 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
 #define MARK(name) do { if (!piped) mark(ctx, name); } while (0)
         if (host_in && !staged_hit) {
             cudaStream_t hs = piped ? ctx->copy_st : ctx->st;
-            CK(cudaMemcpy2DAsync(b.src + (size_t)f0 * d.src_frame, d.src_pitch, bgr + (size_t)f0 * pitch * src_h, pitch,
-                                 (size_t)src_w * 3, (size_t)src_h * nc, cudaMemcpyHostToDevice, hs));
+            CK(h2d_rows(b.src + (size_t)f0 * d.src_frame, bgr + (size_t)f0 * pitch * src_h, pitch, (size_t)src_w * 3,
+                        (size_t)src_h * nc, hs));
             if (piped) {
                 CK(cudaEventRecord(ctx->ev_copy[c], hs));
                 CK(cudaStreamWaitEvent(cs, ctx->ev_copy[c], 0));
