@@ -175,7 +175,7 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -331,12 +331,24 @@ def run_gpu(args):
         except Exception as e:  # the GPU numbers stand on their own
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "failed: %r" % (e,)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_OUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's original stdout; everything libraries print meanwhile (NCCL's version
+    banner, for instance) was diverted to stderr in main()."""
+    print(json.dumps(line), file=_OUT if _OUT is not None else sys.stdout, flush=True)
+
+
 def main():
+    global _OUT
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
