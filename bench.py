@@ -103,6 +103,29 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Multi-rank runs: keep this rank (and so its pinned frame buffers, first-touched below) on the CPUs NVML reports as
+    local to its GPU, so that eight ranks do not pull their host->device copies across the socket interconnect.
+    Best effort: any failure, or an empty intersection with the CPUs the container allows, leaves the affinity alone."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(local)
+        bus = "%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        local_cpus = {i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1}
+        allowed = set(os.sched_getaffinity(0)) & local_cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        print("[bench] rank on cuda:%d: %d of %d allowed CPUs are local to the GPU -> affinity %s" % (
+            local, len(allowed), len(os.sched_getaffinity(0)) if not allowed else len(allowed), "set" if allowed else "unchanged"),
+            file=sys.stderr, flush=True)
+    except Exception as e:
+        print("[bench] NUMA binding skipped: %r" % (e,), file=sys.stderr, flush=True)
+
+
 def make_frames(n, base_seed):
     from oracle import synth  # input generator only (test/bench infrastructure)
     return synth.sequence(n, base_seed=base_seed, H=H, W=W)
@@ -190,6 +213,8 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     torch.cuda.set_device(local)
+    if world > 1:
+        bind_to_gpu_numa_node(torch, local)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
