@@ -190,6 +190,15 @@ LSF_API int lsf_map_size(lsf_ctx *ctx);
  * valid until the next call on the ctx.  Needs LSF_STAGE_GROUND (and LSF_STAGE_DESCRIBE for the descriptors). */
 LSF_API int lsf_pack_kept_records(lsf_ctx *ctx, int frame_base, void **records, int *n_records);
 
+/* First consumer of the path.  Replaces the vote loop of LaneFilterHistogram.generate_measurement_likelihood
+ * (src/lane_filter/include/lane_filter/lane_filter.py:82-102, generateVote :123-155) for every frame of the last batch:
+ * hist[f][i][j] = number of kept ground segments of frame f whose vote (d_i, phi_i) falls into cell
+ * i = floor((d_i - d_min) / delta_d), j = floor((phi_i - phi_min) / delta_phi)   (int32 [n_frames][nd][nphi], host or
+ * device per mem_kind; the measurement likelihood is hist[f] / sum(hist[f])).  d_min .. phi_max, lanewidth and the line
+ * widths are those of lsf_config (identical in the reference's line_sanity and lane_filter defaults).
+ * Needs LSF_STAGE_GROUND in the last batch. */
+LSF_API int lsf_lane_votes(lsf_ctx *ctx, double delta_d, double delta_phi, int nd, int nphi, int mem_kind, int32_t *hist);
+
 /* Forget the previous batch's last frame (start of a new sequence for LSF_STAGE_MATCH_PREV). */
 LSF_API int lsf_reset_sequence(lsf_ctx *ctx);
 

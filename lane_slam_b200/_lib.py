@@ -41,7 +41,7 @@ class LsfSegments(C.Structure):
 _EXPORTS = [
     "lsf_default_config", "lsf_create", "lsf_destroy", "lsf_last_error", "lsf_set_color_transform", "lsf_set_chunk_frames",
     "lsf_front_end_batch", "lsf_prefetch_batch", "lsf_detect_batch", "lsf_describe_batch", "lsf_project_filter_batch",
-    "lsf_knn_hamming", "lsf_pack_kept_records", "lsf_map_clear", "lsf_map_add", "lsf_map_size", "lsf_reset_sequence", "lsf_get_tap", "lsf_image_dims",
+    "lsf_knn_hamming", "lsf_pack_kept_records", "lsf_lane_votes", "lsf_map_clear", "lsf_map_add", "lsf_map_size", "lsf_reset_sequence", "lsf_get_tap", "lsf_image_dims",
     "lsf_last_timings", "lsf_launch_count", "lsf_stream", "lsf_version",
 ]
 
@@ -79,6 +79,7 @@ def load():
     lib.lsf_project_filter_batch.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     lib.lsf_knn_hamming.argtypes = [vp, vp, i32, vp, i32, i32, i32, i32, vp, vp]
     lib.lsf_pack_kept_records.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i32)]
+    lib.lsf_lane_votes.argtypes = [vp, C.c_double, C.c_double, i32, i32, i32, vp]
     lib.lsf_map_clear.argtypes = [vp]
     lib.lsf_map_add.argtypes = [vp, vp, i32, i32]
     lib.lsf_map_size.argtypes = [vp]

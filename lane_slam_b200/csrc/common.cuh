@@ -127,6 +127,8 @@ void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st);      // seeds 
 void launch_lsd_validate(const Dims &d, Buffers &b, cudaStream_t st);  // NFA validation + emit
 void launch_seg_offsets(const Dims &d, Buffers &b, cudaStream_t st);
 void launch_segments(const Dims &d, const CamParams &cam, Buffers &b, int do_ground, cudaStream_t st);
+void launch_lane_votes(const CamParams &cam, int nseg, double delta_d, double delta_phi, int nd, int nphi, const Buffers &b, int *hist,
+                       cudaStream_t st);
 void launch_pack_kept(int nseg, int frame_base, const Buffers &b, u8 *rec, int *count, cudaStream_t st);
 void launch_gray_sobel(const Dims &d, const u8 *gray, short *dx, short *dy, cudaStream_t st);
 void launch_lbd(const Dims &d, const float *lines, const int *frame_of_seg, int nseg_cap, const int *seg_lo_dev,

@@ -86,14 +86,16 @@ __device__ __forceinline__ void vec2ground(const CamParams &cam, float vx, float
     gx = g0 / g2; gy = g1 / g2;
 }
 
-__device__ __forceinline__ u8 sanity_keep(const CamParams &cam, double p1x, double p1y, double p2x, double p2y, int colour)
+// (d_i, phi_i) of a ground segment: fancyFilters (line_sanity_node.py:75-117) == LaneFilterHistogram.generateVote
+// (src/lane_filter/include/lane_filter/lane_filter.py:123-155).  Returns false for colours other than white / yellow.
+__device__ __forceinline__ bool lane_vote(const CamParams &cam, double p1x, double p1y, double p2x, double p2y, int colour,
+                                          double &d_i, double &phi_i)
 {
-    if (p1x < 0 || p2x < 0) return 0;
-    if (colour != LSF_WHITE && colour != LSF_YELLOW) return 0;
+    if (colour != LSF_WHITE && colour != LSF_YELLOW) return false;
     double dx = p2x - p1x, dy = p2y - p1y, nrm = sqrt(dx * dx + dy * dy);
     double tx = dx / nrm, ty = dy / nrm, nx = -ty, ny = tx;
     double d1 = nx * p1x + ny * p1y, d2 = nx * p2x + ny * p2y;
-    double d_i = (d1 + d2) / 2, phi_i = asin(ty);
+    d_i = (d1 + d2) / 2; phi_i = asin(ty);
     if (colour == LSF_WHITE) {
         if (p1x > p2x) d_i = d_i - cam.lw_white;
         else { d_i = -d_i; phi_i = -phi_i; }
@@ -103,8 +105,41 @@ __device__ __forceinline__ u8 sanity_keep(const CamParams &cam, double p1x, doub
         else d_i = -d_i;
         d_i = cam.lanewidth / 2 - d_i;
     }
+    return true;
+}
+
+__device__ __forceinline__ u8 sanity_keep(const CamParams &cam, double p1x, double p1y, double p2x, double p2y, int colour)
+{
+    if (p1x < 0 || p2x < 0) return 0;
+    double d_i, phi_i;
+    if (!lane_vote(cam, p1x, p1y, p2x, p2y, colour, d_i, phi_i)) return 0;
     if (d_i > cam.d_max || d_i < cam.d_min || phi_i < cam.phi_min || phi_i > cam.phi_max) return 0;
     return 1;
+}
+
+// ---- lane-filter measurement votes: histogram of (d_i, phi_i) of the kept segments of every frame ----
+// Replaces the vote loop of LaneFilterHistogram.generate_measurement_likelihood (lane_filter.py:82-102): its colour /
+// x >= 0 / range tests are exactly the line_sanity keep mask.  One thread per segment, atomic counts.
+__global__ void k_lane_votes(CamParams cam, int nseg, double delta_d, double delta_phi, int nd, int nphi,
+                             const u8 *__restrict__ keep, const int *__restrict__ frame, const u8 *__restrict__ color,
+                             const double *__restrict__ ground, int *__restrict__ hist)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nseg || !keep[i]) return;
+    const double2 a = reinterpret_cast<const double2 *>(ground)[2 * (size_t)i], b = reinterpret_cast<const double2 *>(ground)[2 * (size_t)i + 1];
+    double d_i, phi_i;
+    if (!lane_vote(cam, a.x, a.y, b.x, b.y, color[i], d_i, phi_i)) return;
+    const int bi = (int)floor((d_i - cam.d_min) / delta_d), bj = (int)floor((phi_i - cam.phi_min) / delta_phi);
+    if (bi < 0 || bi >= nd || bj < 0 || bj >= nphi) return;   // a vote exactly on the upper edge (the reference raises IndexError)
+    atomicAdd(&hist[((size_t)frame[i] * nd + bi) * nphi + bj], 1);
+}
+
+void launch_lane_votes(const CamParams &cam, int nseg, double delta_d, double delta_phi, int nd, int nphi, const Buffers &b, int *hist,
+                       cudaStream_t st)
+{
+    if (nseg <= 0) return;
+    k_lane_votes<<<(nseg + 127) / 128, 128, 0, st>>>(cam, nseg, delta_d, delta_phi, nd, nphi, b.o_keep, b.o_frame, b.o_color, b.o_ground, hist);
+    ++g_launches;
 }
 
 __global__ void __launch_bounds__(128) k_segments(Dims d, CamParams cam, int do_ground, const LsdSeg *__restrict__ rawseg,

@@ -768,6 +768,29 @@ extern "C" int lsf_pack_kept_records(lsf_ctx *ctx, int frame_base, void **record
     return LSF_OK;
 }
 
+extern "C" int lsf_lane_votes(lsf_ctx *ctx, double delta_d, double delta_phi, int nd, int nphi, int mem_kind, int32_t *hist)
+{
+    if (!ctx || !hist) return LSF_E_ARG;
+    if (!ctx->have_batch || !(ctx->last_stages & LSF_STAGE_GROUND))
+        return fail(ctx, LSF_E_ARG, "lsf_lane_votes: the last batch must have run LSF_STAGE_GROUND");
+    if (!(delta_d > 0) || !(delta_phi > 0) || nd <= 0 || nphi <= 0 || (long long)nd * nphi > (1 << 20))
+        return fail(ctx, LSF_E_ARG, "lsf_lane_votes: bad histogram geometry");
+    CK(cudaSetDevice(ctx->device));
+    const size_t cells = (size_t)ctx->d.n * nd * nphi;
+    int *dh = hist;
+    if (mem_kind != LSF_MEM_DEVICE) {
+        int rc = stage_in(ctx, cells * sizeof(int));
+        if (rc) return rc;
+        dh = (int *)ctx->seg_in;
+    }
+    CK(cudaMemsetAsync(dh, 0, cells * sizeof(int), ctx->st));
+    launch_lane_votes(ctx->cam, ctx->last_S, delta_d, delta_phi, nd, nphi, ctx->b, dh, ctx->st);
+    if (mem_kind != LSF_MEM_DEVICE) CK(cudaMemcpyAsync(hist, dh, cells * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaGetLastError());
+    return LSF_OK;
+}
+
 extern "C" int lsf_map_clear(lsf_ctx *ctx)
 {
     if (!ctx) return LSF_E_ARG;

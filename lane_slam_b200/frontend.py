@@ -200,6 +200,7 @@ class FrontEnd:
         rc = self._lib.lsf_front_end_batch(self._ctx, ptr, n, H, W, W * 3, kind, int(stages), kk, C.byref(seg))
         self._check(rc)
         del dev_ptr
+        self._last_n = n
         S = seg.n_segments
         if kk and kk != 8:
             # library wrote [S][k] densely into buffers shaped [cap][8]: re-view
@@ -272,6 +273,18 @@ class FrontEnd:
     def map_add_device(self, ptr, n):
         """Append n 32-byte descriptors that already live on the device."""
         self._check(self._lib.lsf_map_add(self._ctx, ptr, int(n), MEM_DEVICE))
+
+    def lane_votes(self, delta_d=0.02, delta_phi=0.1):
+        """Vote histograms of the last batch, int32 [n_frames, nd, nphi]: the counts that
+        LaneFilterHistogram.generate_measurement_likelihood (lane_filter.py:82-102) accumulates before normalising.
+        The grid is np.mgrid[d_min:d_max:delta_d, phi_min:phi_max:delta_phi] like the reference's (23 x 30 by default)."""
+        cfg = self.cfg
+        nd = len(np.arange(cfg.d_min, cfg.d_max, delta_d))
+        nphi = len(np.arange(cfg.phi_min, cfg.phi_max, delta_phi))
+        n = self._last_n
+        hist = np.zeros((n, nd, nphi), np.int32)
+        self._check(self._lib.lsf_lane_votes(self._ctx, float(delta_d), float(delta_phi), nd, nphi, MEM_HOST, hist.ctypes.data))
+        return hist
 
     def reset_sequence(self):
         """Start a new sequence for STAGE_MATCH_PREV (forget the previous batch's last frame)."""

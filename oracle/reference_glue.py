@@ -285,6 +285,28 @@ def sanity_keep(points, colors):
     return keep
 
 
+def lane_filter_votes(points, colors, delta_d=0.02, delta_phi=0.1):
+    """Vote counts of LaneFilterHistogram.generate_measurement_likelihood (src/lane_filter/include/lane_filter/
+    lane_filter.py:82-102; generateVote :123-155 has the arithmetic of fancyFilters) for the ground segments of ONE
+    frame -> int array [23, 30] for the default grid np.mgrid[d_min:d_max:delta_d, phi_min:phi_max:delta_phi]
+    (the measurement likelihood is counts / counts.sum(), or None when there is no vote)."""
+    from math import floor
+    d, _ = np.mgrid[D_MIN:D_MAX:delta_d, PHI_MIN:PHI_MAX:delta_phi]
+    counts = np.zeros(d.shape, np.int64)
+    for g, c in zip(points, colors):
+        if c != WHITE and c != YELLOW:
+            continue
+        if g[0] < 0 or g[2] < 0:
+            continue
+        d_i, phi_i, l_i, state = fancy_filters(g[0:2], g[2:4], c)
+        if d_i > D_MAX or d_i < D_MIN or phi_i < PHI_MIN or phi_i > PHI_MAX:
+            continue
+        i = int(floor((d_i - D_MIN) / delta_d))
+        j = int(floor((phi_i - PHI_MIN) / delta_phi))
+        counts[i, j] += 1
+    return counts
+
+
 def front_end_frame(image_cv, detector, gp, img_size, top_cutoff, scale=(1, 1, 1), shift=(0, 0, 0)):
     """detector -> ground_projection -> line_sanity for one frame (show_map_complete.launch:10-43 chain)."""
     r = detect_frame(image_cv, detector, img_size, top_cutoff, scale, shift)

@@ -370,3 +370,20 @@ def test_pack_kept_records_device_equals_host_packing(mods):
     dev = torch.as_tensor(ldist._DeviceBytes(ptr, n * ldist.RECORD_BYTES), device="cuda").cpu().numpy()
     assert np.array_equal(dev, host.view(np.uint8).reshape(-1))
     fe.close()
+
+
+def test_lane_filter_votes(mods):
+    """lsf_lane_votes == the vote loop of LaneFilterHistogram.generate_measurement_likelihood
+    (oracle restatement, pinned to the reference's own class in test_oracle.py) on the GPU's ground segments."""
+    L, cm, rg, synth, cfg = mods
+    frames = np.stack([synth.frame(s) for s in (0, 1, 2, 7, 23, 40, 41, 42)])
+    fe, cam, Hg = _front_end(L, rg, (480, 640), 0, 480, 640, len(frames))
+    b = fe.process(frames, stages=L.STAGE_DETECT | L.STAGE_GROUND)
+    hist = fe.lane_votes()
+    assert hist.shape == (len(frames), 23, 30) and hist.dtype == np.int32
+    for f in range(len(frames)):
+        g = b.frame(f)
+        want = rg.lane_filter_votes(g["ground"], g["color"])
+        assert np.array_equal(hist[f], want), "frame %d" % f
+        assert hist[f].sum() == int(g["keep"].sum())
+    fe.close()

@@ -160,3 +160,17 @@ def test_nfa_known_answers():
     assert lib.orc_nfa(0, 0, 0.125, logNT) == -logNT
     assert abs(lib.orc_nfa(10, 10, 0.125, logNT) - (-logNT - 10 * math.log10(0.125))) < 1e-12
     assert lib.orc_nfa(17, 15, 0.125, logNT) > 0 > lib.orc_nfa(16, 14, 0.125, logNT)
+
+
+def test_golden_lane_filter_votes():
+    """the restated vote loop equals the reference's own LaneFilterHistogram.generate_measurement_
+    likelihood (golden generated by tests/golden/make_golden_lane_filter.py from /root/reference)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lane_filter_votes.npz"))
+    for k in range(len(g["seeds"])):
+        counts = rg.lane_filter_votes(g["ground_%d" % k], g["color_%d" % k])
+        assert counts.shape == (23, 30)
+        ml = g["likelihood_%d" % k]
+        assert counts.sum() > 0
+        assert np.array_equal(counts / counts.sum(), ml)
+        # the votes are exactly the segments line_sanity keeps
+        assert counts.sum() == rg.sanity_keep(g["ground_%d" % k], g["color_%d" % k]).sum()
