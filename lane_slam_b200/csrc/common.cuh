@@ -92,7 +92,8 @@ struct Buffers {
     u32 *corder, *cpos; // [n*3][pixcap]  seed order partitioned by component; position of each entry in order[]
     uint2 *tasks;       // [n*3][LSD_MAXC] {offset into corder, size} of every task (union of components with >= min_reg pixels)
     uint2 *worklist;    // [n*3*LSD_MAXC] (image, task) work list of the growing kernel: big tasks from the front, small from the back
-    int *taskctr;       // [64][4]        per pipeline chunk: big tasks, small tasks, work cursor, candidates
+    int *taskctr;       // [64][8]        per pipeline chunk: big tasks, small tasks, grow cursor, candidates, validate cursor,
+                        //                LBD cursor
     u32 *candrank;      // [n*3][segcap]  position of the candidate's seed in order[] (restores the acceptance order)
     uint4 *reg;         // [n*3][2*pixcap] region point list {idx, xy, g2, angle bits} + scratch
     u32 *usedbits;      // [n*3][ceil(pixcap/32)] USED bitmap, only when it does not fit in shared memory
@@ -132,7 +133,7 @@ void launch_lane_votes(const CamParams &cam, int nseg, double delta_d, double de
 void launch_pack_kept(int nseg, int frame_base, const Buffers &b, u8 *rec, int *count, cudaStream_t st);
 void launch_gray_sobel(const Dims &d, const u8 *gray, short *dx, short *dy, cudaStream_t st);
 void launch_lbd(const Dims &d, const float *lines, const int *frame_of_seg, int nseg_cap, const int *seg_lo_dev,
-                const int *seg_hi_dev, const short *dx, const short *dy, u8 *desc, cudaStream_t st);
+                const int *seg_hi_dev, const short *dx, const short *dy, u8 *desc, int *cursor, cudaStream_t st);
 void launch_project_filter(const CamParams &cam, const float *pixn, const u8 *color, int nseg, double *ground, u8 *keep,
                            cudaStream_t st);
 void launch_knn(const u8 *q, int nq_cap, const int *nq_dev, const u8 *m, int nm, int k, int max_dist, int *idx, int *dist,

@@ -164,7 +164,7 @@ constexpr int LBD_WARPS = 4;
 
 __global__ void __launch_bounds__(LBD_WARPS * 32, 8) k_lbd(Dims d, const float *__restrict__ lines, const int *__restrict__ frame_of_seg,
                                                        int nseg_cap, const int *__restrict__ seg_lo_dev,
-                                                       const int *__restrict__ seg_hi_dev,
+                                                       const int *__restrict__ seg_hi_dev, int *__restrict__ cursor,
                                                        const short2 *__restrict__ dxy, u8 *__restrict__ desc)
 {
     __shared__ float rows[LBD_WARPS][63][4];   // per-row sums scaled by the global Gaussian weight
@@ -173,7 +173,12 @@ __global__ void __launch_bounds__(LBD_WARPS * 32, 8) k_lbd(Dims d, const float *
     const int seg_lo = seg_lo_dev ? *seg_lo_dev : 0;
     const int nseg = min(*seg_hi_dev, nseg_cap);
     const int W = d.w, H = d.h;
-    for (int sidx = seg_lo + blockIdx.x * LBD_WARPS + warp; sidx < nseg; sidx += gridDim.x * LBD_WARPS) {
+    // lines differ a lot in length: warps pull them one at a time
+    while (true) {
+        int sidx = 0;
+        if (lane == 0) sidx = seg_lo + atomicAdd(cursor, 1);
+        sidx = __shfl_sync(0xffffffffu, sidx, 0);
+        if (sidx >= nseg) break;
         // ---- KeyLine fill (octave 0) ----
         float4 ln = reinterpret_cast<const float4 *>(lines)[sidx];
         float e0 = ln.x, e1 = ln.y, e2 = ln.z, e3 = ln.w;
@@ -312,13 +317,13 @@ __global__ void __launch_bounds__(LBD_WARPS * 32, 8) k_lbd(Dims d, const float *
 }
 
 void launch_lbd(const Dims &d, const float *lines, const int *frame_of_seg, int nseg_cap, const int *seg_lo_dev,
-                const int *seg_hi_dev, const short *dx, const short *, u8 *desc, cudaStream_t st)
+                const int *seg_hi_dev, const short *dx, const short *, u8 *desc, int *cursor, cudaStream_t st)
 {
     ensure_lbd_tables();
     int grid = 148 * 8;
     if (nseg_cap < grid * LBD_WARPS) grid = (nseg_cap + LBD_WARPS - 1) / LBD_WARPS;
     if (grid < 1) grid = 1;
-    k_lbd<<<grid, LBD_WARPS * 32, 0, st>>>(d, lines, frame_of_seg, nseg_cap, seg_lo_dev, seg_hi_dev, reinterpret_cast<const short2 *>(dx), desc);
+    k_lbd<<<grid, LBD_WARPS * 32, 0, st>>>(d, lines, frame_of_seg, nseg_cap, seg_lo_dev, seg_hi_dev, cursor, reinterpret_cast<const short2 *>(dx), desc);
     ++g_launches;
 }
 

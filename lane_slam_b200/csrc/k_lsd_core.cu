@@ -1087,13 +1087,18 @@ constexpr int VAL_WARPS = 4;
 
 __global__ void __launch_bounds__(VAL_WARPS * 32, 6) k_lsd_validate(Dims d, const LsdWord *__restrict__ lsdw, const LsdPix *__restrict__ pix,
                                                                    const int *__restrict__ pixcount, const LsdCand *__restrict__ cand,
-                                                                const uint2 *__restrict__ candlist, const int *__restrict__ taskctr,
+                                                                const uint2 *__restrict__ candlist, int *__restrict__ taskctr,
                                                                 LsdSeg *__restrict__ candseg, u8 *__restrict__ candok)
 {
     const int lane = threadIdx.x & 31;
     const int total = min(taskctr[3], d.n * 3 * d.segcap);
-    const int nwarps = gridDim.x * VAL_WARPS;
-    for (int t = blockIdx.x * VAL_WARPS + (threadIdx.x >> 5); t < total; t += nwarps) {
+    // candidates cost between one and 26 rectangle scans: warps pull them one at a time (a static split left 5 % of
+    // the warps active on average, ncu)
+    while (true) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&taskctr[4], 1);
+        t = __shfl_sync(FULL, t, 0);
+        if (t >= total) break;
         uint2 e = candlist[t];
         const int img = (int)e.x, ci = (int)e.y;
         Img im;

@@ -217,7 +217,7 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     CKC(dalloc(&b.order, n * 3 * ctx->pixcap));
     CKC(dalloc(&b.label, n * 3 * ctx->pixcap)); CKC(dalloc(&b.csize, n * 3 * ctx->pixcap)); CKC(dalloc(&b.coff, n * 3 * ctx->pixcap));
     CKC(dalloc(&b.corder, n * 3 * ctx->pixcap)); CKC(dalloc(&b.cpos, n * 3 * ctx->pixcap));
-    CKC(dalloc(&b.tasks, n * 3 * LSD_MAXC)); CKC(dalloc(&b.worklist, n * 3 * LSD_MAXC)); CKC(dalloc(&b.taskctr, 64 * 4));
+    CKC(dalloc(&b.tasks, n * 3 * LSD_MAXC)); CKC(dalloc(&b.worklist, n * 3 * LSD_MAXC)); CKC(dalloc(&b.taskctr, 64 * 8));
     CKC(dalloc(&b.candrank, n * 3 * ctx->segcap));
     CKC(dalloc(&b.reg, n * 3 * ctx->pixcap * 2));
     CKC(dalloc(&b.pixcount, n * 3));
@@ -484,7 +484,7 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
     ctx->last_src = src; ctx->d = d; ctx->have_batch = true;
     if (d.identity_geom) make_tma(ctx, src, n, src_h, src_w, d.src_pitch); else ctx->tma.valid = 0;
     CK(cudaMemsetAsync(b.flags, 0, 4 * sizeof(int), ctx->st));
-    CK(cudaMemsetAsync(b.taskctr, 0, 64 * 4 * sizeof(int), ctx->st));
+    CK(cudaMemsetAsync(b.taskctr, 0, 64 * 8 * sizeof(int), ctx->st));
     CK(cudaMemsetAsync(b.prectr, 0, 64 * sizeof(int), ctx->st));
     const bool describe = (stages & LSF_STAGE_DESCRIBE) != 0, match_prev = (stages & LSF_STAGE_MATCH_PREV) != 0;
     if (match_prev) {
@@ -534,7 +534,7 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
         bc.usedbits += i0 * (size_t)((d.pixcap + 31) / 32);
         bc.pixcount += i0; bc.g2max += i0; bc.cand += i0 * d.segcap; bc.candcount += i0;
         bc.label += i0 * d.pixcap; bc.csize += i0 * d.pixcap; bc.coff += i0 * d.pixcap; bc.corder += i0 * d.pixcap;
-        bc.cpos += i0 * d.pixcap; bc.tasks += i0 * LSD_MAXC; bc.worklist += i0 * LSD_MAXC; bc.taskctr += 4 * c;
+        bc.cpos += i0 * d.pixcap; bc.tasks += i0 * LSD_MAXC; bc.worklist += i0 * LSD_MAXC; bc.taskctr += 8 * c;
         bc.candrank += i0 * d.segcap; bc.candlist += i0 * d.segcap; bc.candseg += i0 * d.segcap; bc.candok += i0 * d.segcap;
         bc.rawseg += i0 * d.segcap; bc.segcount += i0; bc.imgoff += i0; bc.frame_off += f0;
         launch_color_canny(dc, ctx->cp, src + (size_t)f0 * d.src_frame, ctx->tma, b.ctab, bc.planesA, bc.gray, cs);
@@ -557,7 +557,7 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
         launch_segments(dc, ctx->cam, bc, (stages & LSF_STAGE_GROUND) ? 1 : 0, cs);
         MARK("segments");
         if (describe) {
-            launch_lbd(d, b.o_lines, b.o_frame, b.outcap, b.frame_off + f0, b.frame_off + f0 + nc, b.dx, nullptr, b.o_desc, cs);
+            launch_lbd(d, b.o_lines, b.o_frame, b.outcap, b.frame_off + f0, b.frame_off + f0 + nc, b.dx, nullptr, b.o_desc, bc.taskctr + 5, cs);
             if (piped) CK(cudaEventRecord(ctx->ev_lbd[c], cs));
             MARK("lbd");
         }
@@ -681,8 +681,9 @@ extern "C" int lsf_describe_batch(lsf_ctx *ctx, lsf_segments *segs)
     fos[S] = S;
     CK(cudaMemcpyAsync(ctx->seg_in + off_frame, fos.data(), (size_t)(S + 1) * 4, cudaMemcpyHostToDevice, ctx->st));
     launch_gray_sobel(ctx->d, ctx->b.gray, ctx->b.dx, nullptr, ctx->st);
+    CK(cudaMemsetAsync(ctx->b.flags + 3, 0, sizeof(int), ctx->st));      // work cursor of the LBD kernel
     launch_lbd(ctx->d, (const float *)ctx->seg_in, (const int *)(ctx->seg_in + off_frame), S, nullptr, (const int *)(ctx->seg_in + off_n),
-               ctx->b.dx, nullptr, ctx->seg_in + off_desc, ctx->st);
+               ctx->b.dx, nullptr, ctx->seg_in + off_desc, ctx->b.flags + 3, ctx->st);
     CK(cudaMemcpyAsync(segs->desc, ctx->seg_in + off_desc, (size_t)S * 32, out_kind(segs->mem), ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     CK(cudaGetLastError());
