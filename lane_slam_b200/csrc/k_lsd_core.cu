@@ -632,7 +632,7 @@ __device__ __noinline__ double rect_nfa(const Img &im, const Rect &r)
             }
         }
     }
-    alg = __reduce_add_sync(FULL, alg);
+    alg = (int)__reduce_add_sync(FULL, (unsigned)alg);
     return nfa_d(tot, alg, r.p, im.logNT);
 }
 
@@ -689,7 +689,7 @@ __device__ __forceinline__ void setup_img(Img &im, const Dims &d, int img, const
     im.reg = reg ? reg + (size_t)img * 2 * d.pixcap : nullptr;   // second half: scratch of reduce_region_radius
     im.used = nullptr;
     im.cap = d.pixcap;
-    im.logNT = 5.0 * (log10((double)im.W) + log10((double)im.H)) / 2.0 + log10(11.0);
+    im.logNT = d.logNT;
 }
 
 // ---- kernel 0: seed order, fat neighbour records, connected components (fully parallel, one CTA per image) -------
@@ -781,7 +781,7 @@ __global__ void __launch_bounds__(256) k_lsd_index(Dims d, const LsdWord *__rest
     const size_t ibase = (size_t)img * d.pixcap;
     u32 *label = label_ + ibase, *csize = csize_ + ibase, *coff = coff_ + ibase, *corder = corder_ + ibase, *cpos = cpos_ + ibase;
     u32 *ord = order + ibase;
-    const int min_reg = (int)(-im.logNT / log10(22.5 / 180.0));
+    const int min_reg = d.min_reg;
     const double max_grad = sqrt((double)g2max[img] / 4.0);
     const double bin_coef = max_grad > 0 ? 1023.0 / max_grad : 0.0;
     // every warp owns a contiguous segment (multiple of 32) of any n-long sequence
@@ -1001,7 +1001,7 @@ __global__ void __launch_bounds__(32, GROW_PER_SM) k_lsd_grow(Dims d, const LsdW
         __syncwarp();
         for (int i = lane; i < (im.n + 31) / 32; i += 32) im.used[i] = 0;
         __syncwarp();
-        const int min_reg = (int)(-im.logNT / log10(p));
+        const int min_reg = d.min_reg;
         LsdCand *out = cand + (size_t)img * d.segcap;
         u32 *orank = candrank + (size_t)img * d.segcap;
         int ci_next = lane < n ? (int)ord[lane] : -1;

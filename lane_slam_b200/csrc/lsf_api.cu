@@ -434,6 +434,8 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
     d.dh = ctx->cfg.img_h; d.dw = ctx->cfg.img_w; d.top = ctx->cfg.top_cutoff;
     d.h = ctx->h; d.w = ctx->w; d.wp = ctx->wp; d.sh = ctx->sh; d.sw = ctx->sw; d.swp = ctx->swp;
     d.pixcap = ctx->pixcap; d.segcap = ctx->segcap;
+    d.logNT = 5.0 * (log10((double)d.sw) + log10((double)d.sh)) / 2.0 + log10(11.0);
+    d.min_reg = (int)(-d.logNT / log10(22.5 / 180.0));
     d.identity_geom = (d.dh == src_h && d.dw == src_w);
     d.debug = getenv("LSF_TRACE_LSD") ? atoi(getenv("LSF_TRACE_LSD")) : 0;
     for (int i = 0; i < 3; ++i) { ctx->cp.ai_scale[i] = ctx->cfg.ai_scale[i]; ctx->cp.ai_shift[i] = ctx->cfg.ai_shift[i]; }
