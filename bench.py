@@ -297,6 +297,21 @@ def run_gpu(args):
     _, stage_ms, _, _ = timed(dev, args.steps)
     fe.set_chunk_frames(0)
     clocks = sampler.stop() if rank == 0 else None
+    # p50 latency of one frame through the same call (batch = 1, host frame in, segment list out), rank 0 only
+    lat = None
+    if rank == 0:
+        fe1 = L.FrontEnd(dict(L.DEFAULT_DETECTOR_CONFIGURATION), img_size=(H, W), top_cutoff=0, src_size=(H, W), max_batch=1,
+                         device=local, max_segments_per_frame=1024, pinned=True)
+        one = pinned.numpy()
+        ts = []
+        for i in range(230):
+            t0 = time.perf_counter()
+            fe1.process(one[i % n:i % n + 1], stages=stages, k=K_NN)
+            ts.append(time.perf_counter() - t0)
+        fe1.close()
+        ts = np.array(ts[30:]) * 1e3
+        lat = {"batch1_p50_ms": float(np.percentile(ts, 50)), "batch1_p95_ms": float(np.percentile(ts, 95)), "frames": int(len(ts)),
+               "how": "host wall clock around FrontEnd.process of one pinned host frame (all stages, k=2), after 30 warm-up frames"}
     if world > 1:
         t = torch.tensor([dt_dev, dt_e2e, dt_e2e_single], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -344,6 +359,8 @@ def run_gpu(args):
                        "segment lists copied back every step",
                 "single_call_value": total_frames / dt_e2e_single, "single_call_ms_per_step": 1e3 * dt_e2e_single / args.steps},
         "gpu_launches": int(launches),
+        "latency": dict(lat, batch1000_ms_per_frame_amortised=1e3 * dt_dev / args.steps / n,
+                        batch1000_step_ms=1e3 * dt_dev / args.steps) if lat else None,
         "roofline": roofline, "kernels": kernels, "clocks": clocks,
     }
     if world == 1 and not args.no_cpu:
