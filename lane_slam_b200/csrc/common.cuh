@@ -37,6 +37,8 @@ struct Dims {
     int debug;             // LSF_TRACE_LSD: bit 0 device printf of every LSD candidate, bit 1 grow cycle counters
     double logNT;          // LSD: 5 (log10 sw + log10 sh) / 2 + log10 11, evaluated on the host (the reference's libm)
     int min_reg;           // LSD: int(-logNT / log10(22.5 / 180)), smallest region worth a rectangle
+    int grow_per_sm;       // persistent growing warps per SM for this launch (fewer when chunks overlap: leaves registers
+                           // and issue slots to the dense kernels of the other chunk)
     int f0;                // first frame of this launch inside the batch (TMA coordinate, frame ids of the output rows;
                            // every per-frame / per-image buffer is pre-offset to the chunk)
 };

@@ -1177,7 +1177,7 @@ void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st)
         cudaFuncSetAttribute(k_lsd_grow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = smem;
     }
-    const int grid = 148 * GROW_PER_SM;     // persistent single-warp blocks, GROW_PER_SM resident per SM (register cap)
+    const int grid = 148 * (d.grow_per_sm > 0 && d.grow_per_sm < GROW_PER_SM ? d.grow_per_sm : GROW_PER_SM);   // persistent single-warp blocks
     long long *prof = nullptr;
     if (d.debug & 2) { cudaMalloc((void **)&prof, (size_t)wl_cap * 12 * sizeof(long long)); cudaMemsetAsync(prof, 0, (size_t)wl_cap * 12 * sizeof(long long), st); }
     if (used_global)

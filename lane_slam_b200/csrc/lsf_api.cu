@@ -442,7 +442,7 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
     d.identity_color = 1;
     for (int i = 0; i < 3; ++i) if (ctx->cp.ai_scale[i] != 1.f || ctx->cp.ai_shift[i] != 0.f) d.identity_color = 0;
 
-    d.f0 = 0;
+    d.f0 = 0; d.grow_per_sm = 0;
     ctx->n_events = 0;
     mark(ctx, "start");
     int chunk = ctx->cfg.chunk_frames;
@@ -495,6 +495,7 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
     }
     const size_t ps = (size_t)d.h * d.wp, N = (size_t)d.h * d.w;
     const bool piped = nchunks > 1;
+    const int grow_piped = getenv("LSF_GROW_PIPED") ? atoi(getenv("LSF_GROW_PIPED")) : 10;   // measured: 16 -> 10.56 ms, 10 -> 10.10, 8 -> 10.16, 6 -> 10.29
     if (piped) {
         // Chunk pipeline: chunk c is copied on the copy stream while earlier chunks compute on the aux streams
         // (round robin).  The region-growing kernel is a chain of dependent steps that leaves issue slots free,
@@ -525,6 +526,7 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
         }
         Dims dc = d;
         dc.n = nc; dc.f0 = f0;
+        dc.grow_per_sm = piped ? grow_piped : 0;
         Buffers bc = b;
         const size_t i0 = (size_t)3 * f0;
         bc.planesA += (size_t)f0 * PA_COUNT * ps; bc.planesB += (size_t)f0 * PB_COUNT * ps;
