@@ -9,7 +9,9 @@
  * Ownership: the caller allocates every output with an explicit capacity; the library owns
  * only device scratch inside lsf_ctx.  A ctx is single-owner / not re-entrant (the reference
  * admits one processImage_ at a time: src/line_detector/src/line_detector_node.py:129-139);
- * lsf_set_color_transform is the only call allowed concurrently with a batch.
+ * lsf_set_color_transform is the only call allowed concurrently with a batch (from another thread; it swaps the six
+ * values under a lock and the batch snapshots them under the same lock when it starts).  Several contexts -- on the
+ * same device or on different devices -- may live in one process and be driven from different threads.
  */
 #ifndef LSF_H
 #define LSF_H
@@ -38,6 +40,17 @@ typedef enum lsf_status {
 } lsf_status;
 
 typedef enum lsf_mem_kind { LSF_MEM_HOST = 0, LSF_MEM_PINNED = 1, LSF_MEM_DEVICE = 2 } lsf_mem_kind;
+
+/* Order of neighbours of EQUAL Hamming distance in every k-NN result.
+ * LSF_TIES_REFERENCE (default): the order BinaryDescriptorMatcher::knnMatch itself returns, i.e. the discovery order of
+ *   Mihasher(256, 32) (binary_descriptor_matcher.cpp:276, :634-753) -- by (smallest per-byte XOR popcount, first byte
+ *   reaching it, that XOR byte, train index); verified against the reference's compiled code (tests/golden/lbd_reference.npz).
+ * LSF_TIES_INDEX: ascending train index (what cv2.BFMatcher returns). */
+enum { LSF_TIES_REFERENCE = 0, LSF_TIES_INDEX = 1 };
+
+/* Search radius of the matching STAGES (lsf_front_end_batch): Mihasher's D = ceil(256 / 2) (binary_descriptor_matcher.cpp:761);
+ * farther neighbours are reported as -1.  lsf_knn_hamming takes the radius as an argument. */
+#define LSF_MATCH_RADIUS 128
 
 /* Segment.msg:1-3 */
 enum { LSF_WHITE = 0, LSF_YELLOW = 1, LSF_RED = 2 };
@@ -72,7 +85,8 @@ typedef struct lsf_config {
                                     kernels overlap on several streams.  0 = automatic (n/8 for host frames, n/2 for
                                     frames already on the device, one chunk below 64 frames), < 0 = never chunk (one
                                     stream; lsf_last_timings then lists every kernel) */
-    int32_t reserved[6];
+    int32_t tie_order;           /* LSF_TIES_REFERENCE (0, default) or LSF_TIES_INDEX */
+    int32_t reserved[5];
 } lsf_config;
 
 /*
@@ -139,6 +153,13 @@ LSF_API int lsf_set_color_transform(lsf_ctx *ctx, const float scale[3], const fl
 /* Change lsf_config.chunk_frames of a live ctx (same meaning); takes effect at the next batch. */
 LSF_API int lsf_set_chunk_frames(lsf_ctx *ctx, int chunk_frames);
 
+/* Change lsf_config.tie_order of a live ctx. */
+LSF_API int lsf_set_tie_order(lsf_ctx *ctx, int tie_order);
+
+/* Capacities the ctx was created with: segments / LSD support pixels per frame and colour, and output rows per batch
+ * (= what lsf_segments.capacity never needs to exceed). */
+LSF_API int lsf_capacities(const lsf_ctx *ctx, int *max_segments_per_color, int *max_pixels_per_color, int *max_output_rows);
+
 /* Replaces: LineDetectorNode.processImage_ (line_detector_node.py:141-213) for n frames at once,
  * i.e. cv2.resize/crop, AntiInstagram.applyTransform + convertScaleAbs, LineDetectorLSD.setImage and
  * detectLines x3 (line_detector_lsd.py:38-139), normalisation and toSegmentMsg (:195-205, :251-265);
@@ -155,8 +176,11 @@ LSF_API int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int src
  * runs on the ctx's copy stream into the spare staging buffer) so that it overlaps the kernels of the batch being
  * processed.  A following lsf_front_end_batch call with the same `bgr` pointer and geometry consumes the staged
  * frames instead of copying again; up to two batches may be staged ahead.  The caller must keep `bgr` (pinned
- * memory for a truly asynchronous copy) unchanged until that call returns. */
+ * memory for a truly asynchronous copy) unchanged until that call returns.  A staged batch is matched by pointer and
+ * geometry only: any lsf_front_end_batch call on host frames that does not match drops everything staged, and
+ * lsf_cancel_prefetch drops it explicitly (abandoned replay, buffer about to be reused with other contents). */
 LSF_API int lsf_prefetch_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int src_h, int src_w, size_t pitch);
+LSF_API int lsf_cancel_prefetch(lsf_ctx *ctx);
 
 /* = lsf_front_end_batch(..., LSF_STAGE_DETECT, 0, out) */
 LSF_API int lsf_detect_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int src_h, int src_w, size_t pitch,
@@ -173,8 +197,9 @@ LSF_API int lsf_project_filter_batch(lsf_ctx *ctx, const float *pixels_normalize
                                      int mem_kind, double *ground, uint8_t *keep);
 
 /* Replaces: BinaryDescriptorMatcher::knnMatch(query, train, k) (binary_descriptor_matcher.cpp:258-335).
- * Exact brute force over 32-byte codes; rows ascending by distance, ties by ascending train index;
- * neighbours farther than max_dist (Mihasher D = 128; pass 256 for unbounded) are reported as -1. */
+ * Exact brute force over 32-byte codes; rows ascending by distance, ties per lsf_config.tie_order (default: the
+ * reference's own order); neighbours farther than max_dist (Mihasher D = 128 = LSF_MATCH_RADIUS; pass 256 for
+ * unbounded) are reported as -1 (the reference leaves those entries uninitialised). */
 LSF_API int lsf_knn_hamming(lsf_ctx *ctx, const uint8_t *query, int nq, const uint8_t *train, int nm, int k,
                             int max_dist, int mem_kind, int32_t *idx, int32_t *dist);
 
@@ -202,7 +227,9 @@ LSF_API int lsf_lane_votes(lsf_ctx *ctx, double delta_d, double delta_phi, int n
 /* Forget the previous batch's last frame (start of a new sequence for LSF_STAGE_MATCH_PREV). */
 LSF_API int lsf_reset_sequence(lsf_ctx *ctx);
 
-/* Parity taps: copy a dense stage map of frame `frame` of the last batch to host memory `dst`. */
+/* Parity taps: copy a dense stage map of frame `frame` of the last batch to host memory `dst`.  LSF_TAP_IMAGE re-reads
+ * the input frames: for LSF_MEM_DEVICE input the caller must keep them alive until then; it fails with LSF_E_ARG once
+ * a later lsf_prefetch_batch has overwritten the staging buffer that held them. */
 LSF_API int lsf_get_tap(lsf_ctx *ctx, int tap, int frame, void *dst, size_t dst_bytes);
 
 /* Processed-image geometry for an input of src_h x src_w: h = img_h - top_cutoff, w = img_w. */

@@ -7,7 +7,7 @@ descriptors and Hamming association): the plugin class ``LineDetectorB200`` mirr
 touches ``oracle/`` and there is no CPU fallback.
 """
 from ._lib import (LsfError, STAGE_DESCRIBE, STAGE_DETECT, STAGE_GROUND, STAGE_MATCH, STAGE_MATCH_PREV, MEM_DEVICE, MEM_HOST,
-                   LIB_PATH, exported_symbols)
+                   TIES_REFERENCE, TIES_INDEX, MATCH_RADIUS, LIB_PATH, exported_symbols)
 from .frontend import (FrontEnd, SegmentBatch, DEFAULT_DETECTOR_CONFIGURATION, DETECTOR_PARAM_NAMES, COLORS,
                        WHITE, YELLOW, RED, scaled_calibration, check_detector_configuration)
 from .line_detector import LineDetectorB200, Detections, LineDetectorInterface

@@ -7,6 +7,8 @@ LIB_PATH = os.path.join(_HERE, "liblsf.so")
 
 LSF_OK, LSF_E_CONFIG, LSF_E_ARG, LSF_E_CAPACITY, LSF_E_CUDA, LSF_E_NCCL, LSF_E_INTERNAL = 0, -1, -2, -3, -4, -5, -6
 MEM_HOST, MEM_PINNED, MEM_DEVICE = 0, 1, 2
+TIES_REFERENCE, TIES_INDEX = 0, 1
+MATCH_RADIUS = 128
 STAGE_DETECT, STAGE_GROUND, STAGE_DESCRIBE, STAGE_MATCH, STAGE_MATCH_PREV = 1, 2, 4, 8, 16
 TAP = dict(image=0, labels=1, edges=2, bw_white=3, bw_yellow=4, bw_red=5, ec_white=6, ec_yellow=7, ec_red=8,
            gray=9, dx=10, dy=11)
@@ -24,7 +26,7 @@ class LsfConfig(C.Structure):
         ("d_min", C.c_double), ("d_max", C.c_double), ("phi_min", C.c_double), ("phi_max", C.c_double),
         ("max_batch", C.c_int32), ("max_src_h", C.c_int32), ("max_src_w", C.c_int32),
         ("max_segments_per_color", C.c_int32), ("max_pixels_per_color", C.c_int32), ("device", C.c_int32),
-        ("chunk_frames", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("chunk_frames", C.c_int32), ("tie_order", C.c_int32), ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -40,6 +42,7 @@ class LsfSegments(C.Structure):
 
 _EXPORTS = [
     "lsf_default_config", "lsf_create", "lsf_destroy", "lsf_last_error", "lsf_set_color_transform", "lsf_set_chunk_frames",
+    "lsf_set_tie_order", "lsf_capacities", "lsf_cancel_prefetch",
     "lsf_front_end_batch", "lsf_prefetch_batch", "lsf_detect_batch", "lsf_describe_batch", "lsf_project_filter_batch",
     "lsf_knn_hamming", "lsf_pack_kept_records", "lsf_lane_votes", "lsf_map_clear", "lsf_map_add", "lsf_map_size", "lsf_reset_sequence", "lsf_get_tap", "lsf_image_dims",
     "lsf_last_timings", "lsf_launch_count", "lsf_stream", "lsf_version",
@@ -72,6 +75,9 @@ def load():
     lib.lsf_last_error.restype = C.c_char_p
     lib.lsf_set_color_transform.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.lsf_set_chunk_frames.argtypes = [vp, i32]
+    lib.lsf_set_tie_order.argtypes = [vp, i32]
+    lib.lsf_capacities.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    lib.lsf_cancel_prefetch.argtypes = [vp]
     lib.lsf_front_end_batch.argtypes = [vp, vp, i32, i32, i32, sz, i32, i32, i32, C.POINTER(LsfSegments)]
     lib.lsf_prefetch_batch.argtypes = [vp, vp, i32, i32, i32, sz]
     lib.lsf_detect_batch.argtypes = [vp, vp, i32, i32, i32, sz, i32, C.POINTER(LsfSegments)]

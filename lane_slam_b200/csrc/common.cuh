@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <mutex>
 
 #include "../../include/lsf.h"
 
@@ -140,16 +141,38 @@ void launch_lbd(const Dims &d, const float *lines, const int *frame_of_seg, int 
                 const int *seg_hi_dev, const short *dx, const short *dy, u8 *desc, int *cursor, cudaStream_t st);
 void launch_project_filter(const CamParams &cam, const float *pixn, const u8 *color, int nseg, double *ground, u8 *keep,
                            cudaStream_t st);
-void launch_knn(const u8 *q, int nq_cap, const int *nq_dev, const u8 *m, int nm, int k, int max_dist, int *idx, int *dist,
+void launch_knn(const u8 *q, int nq_cap, const int *nq_dev, const u8 *m, int nm, int k, int max_dist, int tie_order, int *idx, int *dist,
                 void *scratch, size_t scratch_bytes, cudaStream_t st);
 size_t knn_scratch_bytes(int nq, int nm, int k);
-void launch_knn_prev(const u8 *desc, const int *frame_off, int f_begin, int n, int k, int max_dist, const u8 *carry, int carry_n,
-                     int *idx, int *dist, cudaStream_t st);
+void launch_knn_prev(const u8 *desc, const int *frame_off, int f_begin, int n, int k, int max_dist, int tie_order, const u8 *carry,
+                     int carry_n, int *idx, int *dist, cudaStream_t st);
 void launch_unpack_plane(const u32 *plane, int h, int w, int wp, u8 *dst, cudaStream_t st);
 void launch_labels_tap(const u32 *planesA_frame, int h, int w, int wp, u8 *dst, cudaStream_t st);
 void launch_image_tap(const Dims &d, const ColorParams &cp, const u8 *src_frame, u8 *dst, cudaStream_t st);
 
-extern long long g_launches;  // kernels launched by this library
+// Kernels launched by this library: every API entry points t_launches at its ctx's counter (several contexts, on the same
+// or on different devices, may be driven from different threads).
+extern thread_local long long *t_launches;
+#define g_launches (*::lsf::t_launches)
+
+// One-time initialisation PER DEVICE (constant tables, >48 KB shared-memory opt-ins): __constant__ / __device__ symbols and
+// function attributes belong to the device's context, so a flag per device ordinal -- not per process -- guards them.
+constexpr int LSF_MAX_DEVICES = 64;
+struct PerDevice {
+    std::mutex mu;
+    size_t level[LSF_MAX_DEVICES] = {};
+    // runs f() when `want` exceeds what was set up on the current device so far (want = 1 for plain once-only tables)
+    template <typename F> void ensure(size_t want, F f)
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= LSF_MAX_DEVICES) dev = 0;
+        std::lock_guard<std::mutex> lk(mu);
+        if (level[dev] >= want) return;
+        f();
+        level[dev] = want;
+    }
+};
 
 // ---- small device helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }

@@ -25,12 +25,12 @@ constexpr int NT = 256;
 
 __constant__ int c_sdiv[256];
 __constant__ int c_hdiv[256];
-static bool g_tabs_ready = false;
+static PerDevice g_tabs_once;
 
 // sdiv / hdiv for the marching kernel (the tiled kernel reads the per-context table, build_color_tables)
 static void ensure_tables()
 {
-    if (g_tabs_ready) return;
+    g_tabs_once.ensure(1, [] {
     int sdiv[256], hdiv[256];
     sdiv[0] = hdiv[0] = 0;
     for (int i = 1; i < 256; ++i) {
@@ -39,7 +39,7 @@ static void ensure_tables()
     }
     cudaMemcpyToSymbol(c_sdiv, sdiv, sizeof(sdiv));
     cudaMemcpyToSymbol(c_hdiv, hdiv, sizeof(hdiv));
-    g_tabs_ready = true;
+    });
 }
 
 __device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }

@@ -140,11 +140,8 @@ __global__ void __launch_bounds__(HT) k_hysteresis(Dims d, int dilate, int strip
 
 void launch_hysteresis(const Dims &d, int dilate, const u32 *planesA, u32 *planesB, cudaStream_t st)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_hysteresis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HYST_SMEM);
-        attr_set = true;
-    }
+    static PerDevice once;
+    once.ensure(1, [] { cudaFuncSetAttribute(k_hysteresis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HYST_SMEM); });
     // rows per strip so that two planes (+2 halo rows each) fit; a whole frame if possible
     size_t row_bytes = (size_t)d.wp * 4 * 2;
     int max_rows = (int)(HYST_SMEM / row_bytes) - 2;

@@ -2,9 +2,14 @@
 //
 // Replaces BinaryDescriptorMatcher::knnMatch (src/line_descriptor/src/binary_descriptor_matcher.cpp:258-335,
 // Mihasher::query :635-753) and the distance kernel match() (src/line_descriptor/src/bitops_custom.hpp:83-96).
-// Contract: ascending distance, ties by ascending train index, neighbours farther than
-// max_dist are not reported (-1).  The multi-index hash is a CPU-side accelerator of the same exact search
-// and is not reproduced.
+// Contract: ascending distance; neighbours farther than max_dist are not reported (-1).  Ties inside one distance come
+// in the reference's own order (default) or by ascending train index (tie_order = 1, what cv2.BFMatcher does).
+// The reference's order is the discovery order of Mihasher(256, 32) (:634-753): one-byte substrings, radius s = 0, 1, ..
+// per substring, substrings k = 0 .. 31 in turn, flip patterns in increasing integer order, bucket members in train order
+// -> rows of equal distance are ordered by ( s* = min_k popc(q[k]^t[k]), k* = first byte reaching s*, q[k*]^t[k*], index ).
+// The hash tables themselves are a CPU-side accelerator of the same exact search and are not reproduced; the key is
+// evaluated only for the few pairs that can still enter a query's top-k list.  Pinned against the compiled reference
+// (tests/golden/lbd_reference.npz).
 //
 // Each thread keeps one query (8 x 32-bit words) in registers; map descriptors are staged through shared
 // memory and broadcast to the warp.  The map is split across gridDim.y so the grid fills the 148 SMs;
@@ -34,10 +39,30 @@ __device__ __forceinline__ int hamming256(const uint4 &qa, const uint4 &qb, cons
     return __popc(ones) + 2 * __popc(twos) + 4 * (__popc(f1) + __popc(f2));
 }
 
+// sort key of a candidate: (distance << 17) | discovery key (s* 4 bits | k* 5 bits | xor byte 8 bits); 0 in index order
+constexpr int KEY_SHIFT = 17;
+__device__ __noinline__ int mih_key(const uint4 &qa, const uint4 &qb, const uint4 &a, const uint4 &b)
+{
+    const u32 x[8] = {qa.x ^ a.x, qa.y ^ a.y, qa.z ^ a.z, qa.w ^ a.w, qb.x ^ b.x, qb.y ^ b.y, qb.z ^ b.z, qb.w ^ b.w};
+    int best = 9, key = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        u32 c = x[w] - ((x[w] >> 1) & 0x55555555u);
+        c = (c & 0x33333333u) + ((c >> 2) & 0x33333333u);
+        c = (c + (c >> 4)) & 0x0f0f0f0fu;                     // popcount of every byte
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int pc = (int)((c >> (8 * j)) & 0xffu);
+            if (pc < best) { best = pc; key = (pc << 13) | ((4 * w + j) << 8) | (int)((x[w] >> (8 * j)) & 0xffu); }
+        }
+    }
+    return key;
+}
+
 template <int K>
 __device__ __forceinline__ void knn_insert(int (&bd)[K], int (&bi)[K], int dd, int idx)
 {
-    // caller guarantees dd < bd[K-1] (strict: an equal distance keeps the earlier, smaller index)
+    // caller guarantees dd < bd[K-1] (strict: an equal key keeps the earlier, smaller index)
 #pragma unroll
     for (int j = K - 1; j > 0; --j) {
         if (bd[j - 1] > dd) { bd[j] = bd[j - 1]; bi[j] = bi[j - 1]; }
@@ -51,7 +76,7 @@ constexpr int QPT = 1;         // queries per thread (2 was measured slower: 0.5
 
 template <int K>
 __global__ void __launch_bounds__(KT) k_knn_partial(const uint4 *__restrict__ q, int nq_cap, const int *__restrict__ nq_dev,
-                                                   const uint4 *__restrict__ m, int nm, int max_dist, int chunk,
+                                                   const uint4 *__restrict__ m, int nm, int max_dist, int tie_order, int chunk,
                                                    int *__restrict__ pidx, int *__restrict__ pdist)
 {
     __shared__ uint4 tile[KTILE * 2];
@@ -81,7 +106,10 @@ __global__ void __launch_bounds__(KT) k_knn_partial(const uint4 *__restrict__ q,
 #pragma unroll
             for (int u = 0; u < QPT; ++u) {
                 const int dd = hamming256(qa[u], qb[u], a, b);
-                if (dd < bd[u][K - 1] && dd <= max_dist) knn_insert<K>(bd[u], bi[u], dd, t0 + j);
+                if (dd <= (bd[u][K - 1] >> KEY_SHIFT) && dd <= max_dist) {       // rare: may enter the list
+                    const int key = (dd << KEY_SHIFT) | (tie_order ? 0 : mih_key(qa[u], qb[u], a, b));
+                    if (key < bd[u][K - 1]) knn_insert<K>(bd[u], bi[u], key, t0 + j);
+                }
             }
         }
     }
@@ -95,7 +123,7 @@ __global__ void __launch_bounds__(KT) k_knn_partial(const uint4 *__restrict__ q,
     }
 }
 
-// merge nsplit*K candidates per query (already ascending inside a split; splits ascend in train index)
+// merge nsplit*K candidates per query (already ascending inside a split; splits ascend in train index); pdist holds sort keys
 __global__ void k_knn_merge(int nq_cap, const int *__restrict__ nq_dev, int nsplit, int K, int k, const int *__restrict__ pidx,
                             const int *__restrict__ pdist, int *__restrict__ idx, int *__restrict__ dist)
 {
@@ -114,7 +142,7 @@ __global__ void k_knn_merge(int nq_cap, const int *__restrict__ nq_dev, int nspl
             if (dd < bestd || (dd == bestd && ii < besti)) { bestd = dd; besti = ii; }
         }
         idx[(size_t)qi * k + r] = besti;
-        dist[(size_t)qi * k + r] = besti >= 0 ? bestd : -1;
+        dist[(size_t)qi * k + r] = besti >= 0 ? (bestd >> KEY_SHIFT) : -1;
         if (besti < 0) {
             for (int r2 = r + 1; r2 < k; ++r2) { idx[(size_t)qi * k + r2] = -1; dist[(size_t)qi * k + r2] = -1; }
             break;
@@ -128,7 +156,7 @@ __global__ void k_knn_merge(int nq_cap, const int *__restrict__ nq_dev, int nspl
 // per frame; frame 0 matches the carry (last frame of the previous batch).  trainIdx is the index inside
 // the previous frame's segment list.
 template <int K>
-__global__ void __launch_bounds__(128) k_knn_prev(const uint4 *__restrict__ desc, const int *__restrict__ frame_off, int f_begin, int k, int max_dist,
+__global__ void __launch_bounds__(128) k_knn_prev(const uint4 *__restrict__ desc, const int *__restrict__ frame_off, int f_begin, int k, int max_dist, int tie_order,
                                                  const uint4 *__restrict__ carry, int carry_n, int *__restrict__ idx,
                                                  int *__restrict__ dist)
 {
@@ -152,28 +180,31 @@ __global__ void __launch_bounds__(128) k_knn_prev(const uint4 *__restrict__ desc
             __syncthreads();
             for (int j = 0; j < m; ++j) {
                 uint4 a = tile[2 * j], b = tile[2 * j + 1];
-                int dd = hamming256(qa, qbv, a, b);
-                if (dd < bd[K - 1] && dd <= max_dist) knn_insert<K>(bd, bi, dd, t0 + j);
+                const int dd = hamming256(qa, qbv, a, b);
+                if (dd <= (bd[K - 1] >> KEY_SHIFT) && dd <= max_dist) {
+                    const int key = (dd << KEY_SHIFT) | (tie_order ? 0 : mih_key(qa, qbv, a, b));
+                    if (key < bd[K - 1]) knn_insert<K>(bd, bi, key, t0 + j);
+                }
             }
         }
         if (qi < q1) {
             for (int j = 0; j < k; ++j) {
                 bool ok = j < K && bi[j < K ? j : 0] >= 0;
                 idx[(size_t)qi * k + j] = ok ? bi[j] : -1;
-                dist[(size_t)qi * k + j] = ok ? bd[j] : -1;
+                dist[(size_t)qi * k + j] = ok ? (bd[j] >> KEY_SHIFT) : -1;
             }
         }
     }
 }
 
-void launch_knn_prev(const u8 *desc, const int *frame_off, int f_begin, int n, int k, int max_dist, const u8 *carry, int carry_n,
-                     int *idx, int *dist, cudaStream_t st)
+void launch_knn_prev(const u8 *desc, const int *frame_off, int f_begin, int n, int k, int max_dist, int tie_order, const u8 *carry,
+                     int carry_n, int *idx, int *dist, cudaStream_t st)
 {
     const uint4 *d4 = (const uint4 *)desc, *c4 = (const uint4 *)carry;
-    if (k <= 1) k_knn_prev<1><<<n, 128, 0, st>>>(d4, frame_off, f_begin, k, max_dist, c4, carry_n, idx, dist);
-    else if (k <= 2) k_knn_prev<2><<<n, 128, 0, st>>>(d4, frame_off, f_begin, k, max_dist, c4, carry_n, idx, dist);
-    else if (k <= 4) k_knn_prev<4><<<n, 128, 0, st>>>(d4, frame_off, f_begin, k, max_dist, c4, carry_n, idx, dist);
-    else k_knn_prev<8><<<n, 128, 0, st>>>(d4, frame_off, f_begin, k, max_dist, c4, carry_n, idx, dist);
+    if (k <= 1) k_knn_prev<1><<<n, 128, 0, st>>>(d4, frame_off, f_begin, k, max_dist, tie_order, c4, carry_n, idx, dist);
+    else if (k <= 2) k_knn_prev<2><<<n, 128, 0, st>>>(d4, frame_off, f_begin, k, max_dist, tie_order, c4, carry_n, idx, dist);
+    else if (k <= 4) k_knn_prev<4><<<n, 128, 0, st>>>(d4, frame_off, f_begin, k, max_dist, tie_order, c4, carry_n, idx, dist);
+    else k_knn_prev<8><<<n, 128, 0, st>>>(d4, frame_off, f_begin, k, max_dist, tie_order, c4, carry_n, idx, dist);
     ++g_launches;
 }
 
@@ -195,7 +226,7 @@ size_t knn_scratch_bytes(int nq, int nm, int k)
     return (size_t)nq * knn_nsplit(nq, nm) * knn_K(k) * 2 * sizeof(int);
 }
 
-void launch_knn(const u8 *q, int nq_cap, const int *nq_dev, const u8 *m, int nm, int k, int max_dist, int *idx, int *dist,
+void launch_knn(const u8 *q, int nq_cap, const int *nq_dev, const u8 *m, int nm, int k, int max_dist, int tie_order, int *idx, int *dist,
                 void *scratch, size_t, cudaStream_t st)
 {
     if (nq_cap <= 0) return;
@@ -206,10 +237,10 @@ void launch_knn(const u8 *q, int nq_cap, const int *nq_dev, const u8 *m, int nm,
     dim3 grid((nq_cap + KT * QPT - 1) / (KT * QPT), nsplit);
     const uint4 *q4 = (const uint4 *)q, *m4 = (const uint4 *)m;
     switch (K) {
-    case 1: k_knn_partial<1><<<grid, KT, 0, st>>>(q4, nq_cap, nq_dev, m4, nm, max_dist, chunk, pidx, pdist); break;
-    case 2: k_knn_partial<2><<<grid, KT, 0, st>>>(q4, nq_cap, nq_dev, m4, nm, max_dist, chunk, pidx, pdist); break;
-    case 4: k_knn_partial<4><<<grid, KT, 0, st>>>(q4, nq_cap, nq_dev, m4, nm, max_dist, chunk, pidx, pdist); break;
-    default: k_knn_partial<8><<<grid, KT, 0, st>>>(q4, nq_cap, nq_dev, m4, nm, max_dist, chunk, pidx, pdist); break;
+    case 1: k_knn_partial<1><<<grid, KT, 0, st>>>(q4, nq_cap, nq_dev, m4, nm, max_dist, tie_order, chunk, pidx, pdist); break;
+    case 2: k_knn_partial<2><<<grid, KT, 0, st>>>(q4, nq_cap, nq_dev, m4, nm, max_dist, tie_order, chunk, pidx, pdist); break;
+    case 4: k_knn_partial<4><<<grid, KT, 0, st>>>(q4, nq_cap, nq_dev, m4, nm, max_dist, tie_order, chunk, pidx, pdist); break;
+    default: k_knn_partial<8><<<grid, KT, 0, st>>>(q4, nq_cap, nq_dev, m4, nm, max_dist, tie_order, chunk, pidx, pdist); break;
     }
     ++g_launches;
     k_knn_merge<<<(nq_cap + 127) / 128, 128, 0, st>>>(nq_cap, nq_dev, nsplit, K, k, pidx, pdist, idx, dist);

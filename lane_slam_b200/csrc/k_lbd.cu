@@ -9,6 +9,7 @@
 // One warp per line: lane h (and h+32) walks row h of the 63-row support region sequentially, so every
 // float accumulation happens in the reference's order (bit-identical sums).
 #include "common.cuh"
+#include "libm_f32.cuh"
 
 namespace lsf {
 
@@ -140,11 +141,11 @@ void launch_gray_sobel(const Dims &d, const u8 *gray, short *dx, short *, cudaSt
 __constant__ float c_gaussL[21];
 __constant__ float c_gaussG[63];
 __constant__ unsigned char c_comb[32][2];
-static bool g_lbd_ready = false;
+static PerDevice g_lbd_once;
 
 static void ensure_lbd_tables()
 {
-    if (g_lbd_ready) return;
+    g_lbd_once.ensure(1, [] {
     float gl[21], gg[63];
     // integer divisions are intentional (binary_descriptor_custom.cpp:227-258)
     double u = (7 * 3 - 1) / 2, sigma = (7 * 2 + 1) / 2, inv = -1 / (2 * sigma * sigma);
@@ -157,7 +158,7 @@ static void ensure_lbd_tables()
     cudaMemcpyToSymbol(c_gaussL, gl, sizeof(gl));
     cudaMemcpyToSymbol(c_gaussG, gg, sizeof(gg));
     cudaMemcpyToSymbol(c_comb, comb, sizeof(comb));
-    g_lbd_ready = true;
+    });
 }
 
 constexpr int LBD_WARPS = 4;
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(LBD_WARPS * 32, 8) k_lbd(Dims d, const float *
         if (e1 >= H) e1 = (float)H - 1.0f;
         if (e3 < 0) e3 = 0;
         if (e3 >= H) e3 = (float)H - 1.0f;
-        float direction = (float)atan2((double)(e3 - e1), (double)(e2 - e0));  // atan2f, correctly rounded
+        const float direction = lmf_atan2f(__fsub_rn(e3, e1), __fsub_rn(e2, e0));   // == glibc atan2f (libm_f32.cuh)
         int px0 = __float2int_rn(e0), py0 = __float2int_rn(e1), px1 = __float2int_rn(e2), py1 = __float2int_rn(e3);
         int len = max(abs(px1 - px0), abs(py1 - py0)) + 1;  // LineIterator(8-connected).count
         const short2 *img = dxy + (size_t)frame_of_seg[sidx] * H * W;
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(LBD_WARPS * 32, 8) k_lbd(Dims d, const float *
         const short halfHeight = 31;
         const short halfWidth = (short)((len - 1) / 2);
         const float mx = (float)(0.5 * (double)(e0 + e2)), my = (float)(0.5 * (double)(e1 + e3));
-        const float dL0 = (float)cos((double)direction), dL1 = (float)sin((double)direction);
+        const float dL0 = lmf_cosf(direction), dL1 = lmf_sinf(direction);           // == glibc cosf / sinf
         const float dO0 = -dL1, dO1 = dL0;
         float s0x = __fadd_rn(__fadd_rn(__fmul_rn(-dL0, (float)halfWidth), __fmul_rn(dL1, (float)halfHeight)), mx);
         float s0y = __fadd_rn(__fsub_rn(__fmul_rn(-dL1, (float)halfWidth), __fmul_rn(dL0, (float)halfHeight)), my);

@@ -145,7 +145,7 @@ __device__ bool double_equal_d(double a, double b)
 // log_gamma of the integers 0..LGTAB-1, evaluated on the host with the same formulas (and the host libm
 // the reference itself runs on); rect_nfa only ever asks for integer arguments.
 constexpr int LGTAB = 16384;
-__device__ const double *g_lgtab;
+__device__ double g_lgtab[LGTAB];
 
 __device__ __forceinline__ double lg_int(int v)
 {
@@ -998,8 +998,11 @@ __global__ void __launch_bounds__(32, GROW_PER_SM) k_lsd_grow(Dims d, const LsdW
         const float2 *seedcs = scs + (size_t)img * d.pixcap;
         const u32 *ord = corder_ + (size_t)img * d.pixcap + off;
         const u32 *opos = cpos_ + (size_t)img * d.pixcap + off;
+        // private shared-memory bitmap: cleared per task.  The global fallback bitmap is shared by all tasks of an image
+        // (they own disjoint components, so they never touch the same pixel) and was cleared once by the host before
+        // the launch -- clearing it here would wipe the USED bits of tasks of the same image running on other blocks.
         __syncwarp();
-        for (int i = lane; i < (im.n + 31) / 32; i += 32) im.used[i] = 0;
+        if (SB) for (int i = lane; i < (im.n + 31) / 32; i += 32) im.used[i] = 0;
         __syncwarp();
         const int min_reg = d.min_reg;
         LsdCand *out = cand + (size_t)img * d.segcap;
@@ -1151,18 +1154,14 @@ __global__ void __launch_bounds__(128) k_lsd_emit(Dims d, const int *__restrict_
 
 void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st)
 {
-    static bool tab_ready = false;
-    static double *d_lgtab = nullptr;
-    if (!tab_ready) {
+    static PerDevice tabs, attr;
+    tabs.ensure(1, [] {
         cudaMemcpyToSymbol(c_sincos_tab, scr::kSinCosTab, sizeof(scr::kSinCosTab));
         std::vector<double> tab(LGTAB);
         tab[0] = 0.0;
         for (int i = 1; i < LGTAB; ++i) tab[i] = log_gamma_d((double)i);
-        cudaMalloc((void **)&d_lgtab, LGTAB * sizeof(double));
-        cudaMemcpy(d_lgtab, tab.data(), LGTAB * sizeof(double), cudaMemcpyHostToDevice);
-        cudaMemcpyToSymbol(g_lgtab, &d_lgtab, sizeof(d_lgtab));
-        tab_ready = true;
-    }
+        cudaMemcpyToSymbol(g_lgtab, tab.data(), LGTAB * sizeof(double));
+    });
     const int nimg = d.n * 3, wl_cap = nimg * MAXC;
     k_lsd_index<<<nimg, 256, 0, st>>>(d, b.lsdw, b.pix, b.pxy, b.pixcount, b.g2max, b.fat, b.order, b.scs, b.label, b.csize, b.coff,
                                       b.corder, b.cpos, b.tasks, b.worklist, wl_cap, b.taskctr, b.candcount);
@@ -1171,12 +1170,11 @@ void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st)
     const int used_words = (d.pixcap + 31) / 32;
     size_t smem = sizeof(GrowSm) + (size_t)used_words * 4;
     u32 *used_global = nullptr;
-    if (smem > 200 * 1024) { smem = sizeof(GrowSm); used_global = b.usedbits; }
-    static size_t attr = 0;
-    if (!used_global && smem > attr) {
-        cudaFuncSetAttribute(k_lsd_grow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = smem;
+    if (smem > 200 * 1024 || getenv("LSF_FORCE_GLOBAL_USED")) {
+        smem = sizeof(GrowSm); used_global = b.usedbits;
+        cudaMemsetAsync(b.usedbits, 0, (size_t)nimg * used_words * sizeof(u32), st);
     }
+    if (!used_global) attr.ensure(smem, [&] { cudaFuncSetAttribute(k_lsd_grow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
     const int grid = 148 * (d.grow_per_sm > 0 && d.grow_per_sm < GROW_PER_SM ? d.grow_per_sm : GROW_PER_SM);   // persistent single-warp blocks
     long long *prof = nullptr;
     if (d.debug & 2) { cudaMalloc((void **)&prof, (size_t)wl_cap * 12 * sizeof(long long)); cudaMemsetAsync(prof, 0, (size_t)wl_cap * 12 * sizeof(long long), st); }

@@ -542,17 +542,14 @@ static size_t lsd_pre_smem(const Dims &d)
 void launch_lsd_pre(const Dims &d, const u32 *planesB, Buffers &b, cudaStream_t st)
 {
     size_t smem = lsd_pre_smem(d);
-    static size_t attr = 0;
-    if (smem > attr) {
-        cudaFuncSetAttribute(k_lsd_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = smem;
-    }
+    static PerDevice attr, attr2;
     // smallest integer g2 with sqrt(g2/4.0) > rho, rho = 2/sin(22.5 deg)   (ll_angle threshold)
     const double rho = 2.0 / sin(3.14159265358979323846 * 22.5 / 180.0);
     u32 g2_min = 0;
     while (!(sqrt((double)g2_min / 4.0) > rho)) ++g2_min;
     const size_t smem2 = NW * (sizeof(PreSm) + (size_t)16 * d.wp * 4);
     if (getenv("LSF_PRE_V1") || smem2 > 200 * 1024) {     // v1: frames wider than ~12 000 pixels (and A/B runs)
+        attr.ensure(smem, [&] { cudaFuncSetAttribute(k_lsd_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
         k_lsd_pre<<<d.n * 3, PT, smem, st>>>(d, g2_min, planesB, b.lsdw, b.pix, b.pxy, b.pixcount, b.g2max, b.flags);
         ++g_launches;
         return;
@@ -560,11 +557,7 @@ void launch_lsd_pre(const Dims &d, const u32 *planesB, Buffers &b, cudaStream_t 
     const int nbands = (d.sh + BR - 1) / BR;
     const long long nrow = (long long)d.n * 3 * nbands;
     const int grid_a = (int)std::min<long long>((nrow + NW - 1) / NW, 148 * 8);
-    static size_t attr2 = 0;
-    if (smem2 > attr2) {
-        cudaFuncSetAttribute(k_lsd_pre_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-        attr2 = smem2;
-    }
+    attr2.ensure(smem2, [&] { cudaFuncSetAttribute(k_lsd_pre_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); });
     k_lsd_pre_a<<<grid_a, PT, smem2, st>>>(d, g2_min, nbands, planesB, b.lsdw, b.preact, b.prectr, b.prepatch);
     k_lsd_pre_b<<<d.n * 3, PT, 0, st>>>(d, b.lsdw, b.pixcount, b.g2max, b.flags);
     k_lsd_pre_c<<<148 * 8, PT, 0, st>>>(d, nbands, b.lsdw, b.preact, b.prectr, b.prepatch, b.pix, b.pxy, b.g2max);

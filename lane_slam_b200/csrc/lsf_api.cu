@@ -8,8 +8,11 @@
 
 #include "common.cuh"
 
+#include <mutex>
+
 namespace lsf {
-long long g_launches = 0;
+static thread_local long long t_launch_sink = 0;
+thread_local long long *t_launches = &t_launch_sink;
 }
 using namespace lsf;
 
@@ -60,7 +63,9 @@ struct lsf_ctx {
     // timing
     std::vector<StageTime> events;
     int n_events;
-    long long launches0;
+    long long launches;          // kernels launched on behalf of this ctx
+    std::mutex ai_mu;            // guards cfg.ai_scale / ai_shift (lsf_set_color_transform may run concurrently with a batch)
+    bool last_src_valid;         // LSF_TAP_IMAGE: the frames of the last batch are still where last_src points
     std::string err;
 };
 
@@ -74,6 +79,9 @@ struct lsf_ctx {
             return LSF_E_CUDA;                                                                         \
         }                                                                                              \
     } while (0)
+
+// entry of every call that touches the device: select the ctx's device, count launches on the ctx
+#define ENTER(ctx) do { CK(cudaSetDevice((ctx)->device)); lsf::t_launches = &(ctx)->launches; } while (0)
 
 static int fail(lsf_ctx *ctx, int code, const std::string &msg)
 {
@@ -159,6 +167,7 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
         if (e_ != cudaSuccess) return bail(LSF_E_CUDA, std::string(#call " failed: ") + cudaGetErrorString(e_)); \
     } while (0)
     CKC(cudaSetDevice(ctx->device));
+    lsf::t_launches = &ctx->launches;
     CKC(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) CKC(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
@@ -231,7 +240,7 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     CKC(dalloc(&b.segcount, n * 3));
     CKC(dalloc(&b.frame_off, (n + 1) + n * 3));
     b.imgoff = b.frame_off + (n + 1);
-    CKC(dalloc(&b.flags, 4));
+    CKC(dalloc(&b.flags, 8));
     b.outcap = (int)std::min<size_t>(n * 3 * ctx->segcap, (size_t)1 << 30);
     const size_t oc = b.outcap;
     CKC(dalloc(&b.o_color, oc)); CKC(dalloc(&b.o_lines, oc * 4)); CKC(dalloc(&b.o_normals, oc * 2));
@@ -240,9 +249,10 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     CKC(dalloc(&b.o_frame, oc));
     b.o_midx = nullptr; b.o_mdist = nullptr;
     CKC(cudaMallocHost((void **)&ctx->h_small, (n * 3 + n + 1 + 4) * sizeof(int)));
-    CKC(cudaMemsetAsync(b.flags, 0, 4 * sizeof(int), ctx->st));
+    CKC(cudaMemsetAsync(b.flags, 0, 8 * sizeof(int), ctx->st));
     CKC(cudaStreamSynchronize(ctx->st));
-    ctx->launches0 = g_launches;
+    ctx->launches = 0;
+    ctx->last_src_valid = false;
     *out = ctx;
     return LSF_OK;
 #undef CKC
@@ -279,6 +289,8 @@ extern "C" const char *lsf_last_error(const lsf_ctx *ctx) { return ctx ? ctx->er
 extern "C" int lsf_set_color_transform(lsf_ctx *ctx, const float scale[3], const float shift[3])
 {
     if (!ctx || !scale || !shift) return LSF_E_ARG;
+    // the six values change together: a batch that starts meanwhile sees either the old or the new transform, never a mix
+    std::lock_guard<std::mutex> lk(ctx->ai_mu);
     for (int i = 0; i < 3; ++i) { ctx->cfg.ai_scale[i] = scale[i]; ctx->cfg.ai_shift[i] = shift[i]; }
     return LSF_OK;
 }
@@ -287,6 +299,22 @@ extern "C" int lsf_set_chunk_frames(lsf_ctx *ctx, int chunk_frames)
 {
     if (!ctx) return LSF_E_ARG;
     ctx->cfg.chunk_frames = chunk_frames;
+    return LSF_OK;
+}
+
+extern "C" int lsf_set_tie_order(lsf_ctx *ctx, int tie_order)
+{
+    if (!ctx || (tie_order != LSF_TIES_REFERENCE && tie_order != LSF_TIES_INDEX)) return LSF_E_ARG;
+    ctx->cfg.tie_order = tie_order;
+    return LSF_OK;
+}
+
+extern "C" int lsf_capacities(const lsf_ctx *ctx, int *max_segments_per_color, int *max_pixels_per_color, int *max_output_rows)
+{
+    if (!ctx) return LSF_E_ARG;
+    if (max_segments_per_color) *max_segments_per_color = ctx->segcap;
+    if (max_pixels_per_color) *max_pixels_per_color = ctx->pixcap;
+    if (max_output_rows) *max_output_rows = ctx->b.outcap;
     return LSF_OK;
 }
 
@@ -368,7 +396,7 @@ extern "C" int lsf_last_timings(lsf_ctx *ctx, const char **names, float *ms, int
     return n;
 }
 
-extern "C" long long lsf_launch_count(const lsf_ctx *ctx) { return ctx ? g_launches - ctx->launches0 : g_launches; }
+extern "C" long long lsf_launch_count(const lsf_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" void *lsf_stream(lsf_ctx *ctx) { return ctx ? (void *)ctx->st : nullptr; }
 extern "C" const char *lsf_version(void) { return "lsf 0.1 (sm_100a)"; }
 
@@ -385,14 +413,24 @@ extern "C" int lsf_prefetch_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int s
     if (!bgr || n <= 0 || n > ctx->max_batch || src_h <= 0 || src_w <= 0 || src_h > ctx->max_src_h || src_w > ctx->max_src_w ||
         pitch < (size_t)src_w * 3)
         return fail(ctx, LSF_E_ARG, "lsf_prefetch_batch: bad frames / geometry");
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     if (!ctx->stage_buf[1]) CK(cudaMalloc((void **)&ctx->stage_buf[1], (size_t)ctx->max_batch * ctx->max_src_h * ctx->max_src_w * 3));
     // the staging buffer that is not holding an unconsumed batch; the oldest one if both do
     int slot = !ctx->staged[0].valid ? 0 : !ctx->staged[1].valid ? 1 : (ctx->staged[0].seq < ctx->staged[1].seq ? 0 : 1);
     lsf_ctx::Staged &sg = ctx->staged[slot];
+    if (ctx->last_src == ctx->stage_buf[slot]) ctx->last_src_valid = false;   // the frames of the last batch are overwritten
     CK(h2d_rows(ctx->stage_buf[slot], bgr, pitch, (size_t)src_w * 3, (size_t)src_h * n, ctx->copy_st));
     CK(cudaEventRecord(sg.ev, ctx->copy_st));
     sg.host = bgr; sg.n = n; sg.h = src_h; sg.w = src_w; sg.pitch = pitch; sg.valid = true; sg.seq = ++ctx->stage_seq;
+    return LSF_OK;
+}
+
+extern "C" int lsf_cancel_prefetch(lsf_ctx *ctx)
+{
+    if (!ctx) return LSF_E_ARG;
+    ENTER(ctx);
+    CK(cudaStreamSynchronize(ctx->copy_st));
+    ctx->staged[0].valid = ctx->staged[1].valid = false;
     return LSF_OK;
 }
 
@@ -427,7 +465,7 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
     if ((stages & LSF_STAGE_MATCH) && (stages & LSF_STAGE_MATCH_PREV))
         return fail(ctx, LSF_E_ARG, "lsf_front_end_batch: choose one of LSF_STAGE_MATCH / LSF_STAGE_MATCH_PREV");
     if (any_match && (k < 1 || k > 8)) return fail(ctx, LSF_E_ARG, "lsf_front_end_batch: k must be 1..8");
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     Buffers &b = ctx->b;
     Dims d;
     d.n = n; d.src_h = src_h; d.src_w = src_w;
@@ -438,7 +476,10 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
     d.min_reg = (int)(-d.logNT / log10(22.5 / 180.0));
     d.identity_geom = (d.dh == src_h && d.dw == src_w);
     d.debug = getenv("LSF_TRACE_LSD") ? atoi(getenv("LSF_TRACE_LSD")) : 0;
-    for (int i = 0; i < 3; ++i) { ctx->cp.ai_scale[i] = ctx->cfg.ai_scale[i]; ctx->cp.ai_shift[i] = ctx->cfg.ai_shift[i]; }
+    {   // snapshot of the colour transform for this batch (lsf_set_color_transform may be called from another thread)
+        std::lock_guard<std::mutex> lk(ctx->ai_mu);
+        for (int i = 0; i < 3; ++i) { ctx->cp.ai_scale[i] = ctx->cfg.ai_scale[i]; ctx->cp.ai_shift[i] = ctx->cfg.ai_shift[i]; }
+    }
     d.identity_color = 1;
     for (int i = 0; i < 3; ++i) if (ctx->cp.ai_scale[i] != 1.f || ctx->cp.ai_shift[i] != 0.f) d.identity_color = 0;
 
@@ -473,19 +514,23 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
             ctx->staged[hit].valid = false;
             CK(cudaStreamWaitEvent(ctx->st, ctx->staged[hit].ev, 0));
         } else {
-            // copy now, into a staging buffer that holds nothing staged (drop the oldest staged batch if both do)
-            int slot = !ctx->staged[0].valid ? 0 : (ctx->stage_buf[1] && !ctx->staged[1].valid) ? 1 : 0;
-            if (ctx->staged[slot].valid) { CK(cudaStreamSynchronize(ctx->copy_st)); ctx->staged[slot].valid = false; }
-            b.src = ctx->stage_buf[slot];
+            // A host batch that was not staged: whatever is still staged belongs to a replay that was abandoned (a staged
+            // entry is matched by pointer + geometry only, so it must not survive to meet a reused buffer with new
+            // contents).  Drop it, then copy now.
+            if (ctx->staged[0].valid || ctx->staged[1].valid) {
+                CK(cudaStreamSynchronize(ctx->copy_st));
+                ctx->staged[0].valid = ctx->staged[1].valid = false;
+            }
+            b.src = ctx->stage_buf[0];
         }
         src = b.src;
     }
     if (chunk < 0 || chunk > n || (d.debug & 2)) chunk = n;
     if ((n + chunk - 1) / chunk > 64) chunk = (n + 63) / 64;
     const int nchunks = (n + chunk - 1) / chunk;
-    ctx->last_src = src; ctx->d = d; ctx->have_batch = true;
+    ctx->last_src = src; ctx->last_src_valid = true; ctx->d = d; ctx->have_batch = true;
     if (d.identity_geom) make_tma(ctx, src, n, src_h, src_w, d.src_pitch); else ctx->tma.valid = 0;
-    CK(cudaMemsetAsync(b.flags, 0, 4 * sizeof(int), ctx->st));
+    CK(cudaMemsetAsync(b.flags, 0, 8 * sizeof(int), ctx->st));
     CK(cudaMemsetAsync(b.taskctr, 0, 64 * 8 * sizeof(int), ctx->st));
     CK(cudaMemsetAsync(b.prectr, 0, 64 * sizeof(int), ctx->st));
     const bool describe = (stages & LSF_STAGE_DESCRIBE) != 0, match_prev = (stages & LSF_STAGE_MATCH_PREV) != 0;
@@ -567,7 +612,7 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
         }
         if (match_prev) {
             if (piped && c > 0) CK(cudaStreamWaitEvent(cs, ctx->ev_lbd[c - 1], 0));   // descriptors of frame f0 - 1
-            launch_knn_prev(b.o_desc, b.frame_off, f0, nc, k, 256, ctx->carry, ctx->carry_n, b.o_midx, b.o_mdist, cs);
+            launch_knn_prev(b.o_desc, b.frame_off, f0, nc, k, LSF_MATCH_RADIUS, ctx->cfg.tie_order, ctx->carry, ctx->carry_n, b.o_midx, b.o_mdist, cs);
             MARK("knn_prev");
         }
         if (piped) {
@@ -589,6 +634,8 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
                                                        " exceed max_pixels_per_color = " + std::to_string(ctx->pixcap));
     if (flags[1]) return fail(ctx, LSF_E_CAPACITY, "segments of one colour image = " + std::to_string(flags[1]) +
                                                        " exceed max_segments_per_color = " + std::to_string(ctx->segcap));
+    if (flags[2]) return fail(ctx, LSF_E_CAPACITY, "segments of the batch = " + std::to_string(flags[2]) +
+                                                       " exceed the output row capacity " + std::to_string(b.outcap));
     const int S = hs[n * 3 + n];
     out->n_frames = n; out->n_segments = S;
     ctx->last_S = S; ctx->last_stages = stages;
@@ -600,7 +647,7 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
         int rc = ensure_knn(ctx, S, ctx->map_n, k);
         if (rc) return rc;
         if (!b.o_midx) { CK(dalloc(&b.o_midx, (size_t)b.outcap * 8)); CK(dalloc(&b.o_mdist, (size_t)b.outcap * 8)); }
-        launch_knn(b.o_desc, S, nullptr, ctx->map, ctx->map_n, k, 256, b.o_midx, b.o_mdist, ctx->knn_scratch, ctx->knn_scratch_cap, ctx->st);
+        launch_knn(b.o_desc, S, nullptr, ctx->map, ctx->map_n, k, LSF_MATCH_RADIUS, ctx->cfg.tie_order, b.o_midx, b.o_mdist, ctx->knn_scratch, ctx->knn_scratch_cap, ctx->st);
         mark(ctx, "knn");
     }
     if (stages & LSF_STAGE_MATCH_PREV) {
@@ -661,7 +708,7 @@ extern "C" int lsf_describe_batch(lsf_ctx *ctx, lsf_segments *segs)
     if (!ctx->have_batch) return fail(ctx, LSF_E_ARG, "lsf_describe_batch: no frames resident (call lsf_detect_batch first)");
     if (!segs->lines_px || !segs->frame_offset || !segs->desc) return fail(ctx, LSF_E_ARG, "lsf_describe_batch: lines_px, frame_offset and desc are required");
     if (segs->n_frames != ctx->d.n) return fail(ctx, LSF_E_ARG, "lsf_describe_batch: n_frames differs from the resident batch");
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     const int S = segs->n_segments, n = ctx->d.n;
     if (S <= 0) return LSF_OK;
     // layout of the staging buffer: lines f32[S][4] | frame_of_seg i32[S] | nseg i32 | desc u8[S][32]
@@ -700,7 +747,7 @@ extern "C" int lsf_project_filter_batch(lsf_ctx *ctx, const float *pixn, const u
     if (!ctx) return LSF_E_ARG;
     if (n_seg < 0 || (n_seg > 0 && (!pixn || !color || !ground || !keep))) return fail(ctx, LSF_E_ARG, "lsf_project_filter_batch: null argument");
     if (n_seg == 0) return LSF_OK;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     const size_t S = n_seg;
     if (mem_kind == LSF_MEM_DEVICE) {
         launch_project_filter(ctx->cam, pixn, color, n_seg, ground, keep, ctx->st);
@@ -727,7 +774,7 @@ extern "C" int lsf_knn_hamming(lsf_ctx *ctx, const uint8_t *query, int nq, const
     if (nq < 0 || nm < 0 || k < 1 || k > 8) return fail(ctx, LSF_E_ARG, "lsf_knn_hamming: bad sizes (k must be 1..8)");
     if (nq == 0) return LSF_OK;
     if (!query || !idx || !dist || (nm > 0 && !train)) return fail(ctx, LSF_E_ARG, "lsf_knn_hamming: null argument");
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     ctx->n_events = 0;
     const size_t Q = nq, M = nm;
     const u8 *dq, *dm; int *di, *dd;
@@ -744,7 +791,7 @@ extern "C" int lsf_knn_hamming(lsf_ctx *ctx, const uint8_t *query, int nq, const
     int rc = ensure_knn(ctx, nq, nm > 0 ? nm : 1, k);
     if (rc) return rc;
     mark(ctx, "start");
-    launch_knn(dq, nq, nullptr, dm, nm, k, max_dist, di, dd, ctx->knn_scratch, ctx->knn_scratch_cap, ctx->st);
+    launch_knn(dq, nq, nullptr, dm, nm, k, max_dist, ctx->cfg.tie_order, di, dd, ctx->knn_scratch, ctx->knn_scratch_cap, ctx->st);
     mark(ctx, "knn");
     if (mem_kind != LSF_MEM_DEVICE) {
         CK(cudaMemcpyAsync(idx, di, Q * k * 4, cudaMemcpyDeviceToHost, ctx->st));
@@ -760,10 +807,10 @@ extern "C" int lsf_pack_kept_records(lsf_ctx *ctx, int frame_base, void **record
     if (!ctx || !records || !n_records) return LSF_E_ARG;
     if (!ctx->have_batch || !(ctx->last_stages & LSF_STAGE_GROUND))
         return fail(ctx, LSF_E_ARG, "lsf_pack_kept_records: the last batch must have run LSF_STAGE_GROUND");
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     if (!ctx->kept_rec) CK(cudaMalloc((void **)&ctx->kept_rec, (size_t)ctx->b.outcap * 72 + 16));
     if (!(ctx->last_stages & LSF_STAGE_DESCRIBE)) CK(cudaMemsetAsync(ctx->b.o_desc, 0, (size_t)ctx->last_S * 32, ctx->st));
-    int *cnt = ctx->b.flags + 2;     // flags[2] is free after the batch
+    int *cnt = ctx->b.flags + 4;     // its own counter (flags[2] reports output-row overflow of the batch)
     launch_pack_kept(ctx->last_S, frame_base, ctx->b, ctx->kept_rec, cnt, ctx->st);
     CK(cudaMemcpyAsync(ctx->h_small, cnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
@@ -780,7 +827,7 @@ extern "C" int lsf_lane_votes(lsf_ctx *ctx, double delta_d, double delta_phi, in
         return fail(ctx, LSF_E_ARG, "lsf_lane_votes: the last batch must have run LSF_STAGE_GROUND");
     if (!(delta_d > 0) || !(delta_phi > 0) || nd <= 0 || nphi <= 0 || (long long)nd * nphi > (1 << 20))
         return fail(ctx, LSF_E_ARG, "lsf_lane_votes: bad histogram geometry");
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     const size_t cells = (size_t)ctx->d.n * nd * nphi;
     int *dh = hist;
     if (mem_kind != LSF_MEM_DEVICE) {
@@ -816,7 +863,7 @@ extern "C" int lsf_map_add(lsf_ctx *ctx, const uint8_t *desc, int n, int mem_kin
 {
     if (!ctx || n < 0 || (n > 0 && !desc)) return LSF_E_ARG;
     if (n == 0) return LSF_OK;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     if (ctx->map_n + n > ctx->map_cap) {
         int ncap = std::max(ctx->map_cap * 2, ctx->map_n + n);
         ncap = std::max(ncap, 4096);
@@ -841,7 +888,7 @@ extern "C" int lsf_get_tap(lsf_ctx *ctx, int tap, int frame, void *dst, size_t d
     if (!ctx->have_batch) return fail(ctx, LSF_E_ARG, "lsf_get_tap: no batch processed yet");
     const Dims &d = ctx->d;
     if (frame < 0 || frame >= d.n) return fail(ctx, LSF_E_ARG, "lsf_get_tap: frame out of range");
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     const size_t N = (size_t)d.h * d.w, ps = (size_t)d.h * d.wp;
     size_t need = tap == LSF_TAP_IMAGE ? N * 3 : (tap == LSF_TAP_DX || tap == LSF_TAP_DY) ? N * 2 : N;
     if (dst_bytes < need) return fail(ctx, LSF_E_CAPACITY, "lsf_get_tap: need " + std::to_string(need) + " bytes");
@@ -855,7 +902,9 @@ extern "C" int lsf_get_tap(lsf_ctx *ctx, int tap, int frame, void *dst, size_t d
     const u32 *pb = ctx->b.planesB + (size_t)frame * PB_COUNT * ps;
     const void *srcp = ctx->tap_tmp;
     switch (tap) {
-    case LSF_TAP_IMAGE: launch_image_tap(d, ctx->cp, ctx->last_src + (size_t)frame * d.src_frame, ctx->tap_tmp, ctx->st); break;
+    case LSF_TAP_IMAGE:
+        if (!ctx->last_src_valid) return fail(ctx, LSF_E_ARG, "lsf_get_tap: the frames of the last batch were overwritten by a later lsf_prefetch_batch");
+        launch_image_tap(d, ctx->cp, ctx->last_src + (size_t)frame * d.src_frame, ctx->tap_tmp, ctx->st); break;
     case LSF_TAP_LABELS: launch_labels_tap(pa, d.h, d.w, d.wp, ctx->tap_tmp, ctx->st); break;
     case LSF_TAP_EDGES: launch_unpack_plane(pb + PB_EDGE * ps, d.h, d.w, d.wp, ctx->tap_tmp, ctx->st); break;
     case LSF_TAP_BW_WHITE: case LSF_TAP_BW_YELLOW: case LSF_TAP_BW_RED:

@@ -12,8 +12,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (LsfConfig, LsfError, LsfSegments, MEM_DEVICE, MEM_HOST, STAGE_DESCRIBE, STAGE_DETECT,
-                   STAGE_GROUND, STAGE_MATCH, STAGE_MATCH_PREV, TAP)
+from ._lib import (LsfConfig, LsfError, LsfSegments, MATCH_RADIUS, MEM_DEVICE, MEM_HOST, STAGE_DESCRIBE, STAGE_DETECT,
+                   STAGE_GROUND, STAGE_MATCH, STAGE_MATCH_PREV, TAP, TIES_INDEX, TIES_REFERENCE)
 
 WHITE, YELLOW, RED = 0, 1, 2          # src/duckietown_msgs/msg/Segment.msg:1-3
 COLORS = ("white", "yellow", "red")
@@ -87,7 +87,7 @@ class FrontEnd:
     def __init__(self, configuration=None, img_size=(120, 160), top_cutoff=40, camera=None, homography=None,
                  src_size=(480, 640), max_batch=1, device=0, ai_scale=(1, 1, 1), ai_shift=(0, 0, 0),
                  max_segments_per_color=0, max_pixels_per_color=0, max_segments_per_frame=1024, pinned=False,
-                 chunk_frames=0):
+                 chunk_frames=0, tie_order=_lib.TIES_REFERENCE):
         self._lib = _lib.load()
         conf = check_detector_configuration(configuration if configuration is not None
                                             else DEFAULT_DETECTOR_CONFIGURATION)
@@ -123,6 +123,7 @@ class FrontEnd:
         cfg.max_pixels_per_color = int(max_pixels_per_color)
         cfg.device = int(device)
         cfg.chunk_frames = int(chunk_frames)   # 0 auto, < 0 one stream (per-kernel timings), > 0 frames per pipeline chunk
+        cfg.tie_order = int(tie_order)         # order of equal-distance neighbours: the reference's (Mihasher) or ascending index
         self.cfg = cfg
         self.img_size, self.top_cutoff, self.max_batch = tuple(img_size), int(top_cutoff), int(max_batch)
         self._ctx = C.c_void_p()
@@ -135,7 +136,12 @@ class FrontEnd:
         h, w, sh, sw = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         self._lib.lsf_image_dims(self._ctx, C.byref(h), C.byref(w), C.byref(sh), C.byref(sw))
         self.h, self.w, self.lsd_h, self.lsd_w = h.value, w.value, sh.value, sw.value
-        self._cap = int(max_segments_per_frame) * self.max_batch
+        segcap, pixcap, outcap = C.c_int(), C.c_int(), C.c_int()
+        self._lib.lsf_capacities(self._ctx, C.byref(segcap), C.byref(pixcap), C.byref(outcap))
+        self.max_segments_per_color, self.max_pixels_per_color, self.max_output_rows = segcap.value, pixcap.value, outcap.value
+        # host output rows: a starting size; process() grows the buffers up to the library's own row capacity and
+        # retries when a batch holds more (the reference's detector returns however many lines it finds)
+        self._cap = max(1, min(int(max_segments_per_frame) * self.max_batch, self.max_output_rows))
         self._pinned = pinned
         self._host = None
         self._dev = None
@@ -198,8 +204,14 @@ class FrontEnd:
             setattr(seg, name, a[name].ctypes.data)
         kk = int(k) if (stages & (STAGE_MATCH | STAGE_MATCH_PREV)) else 0
         rc = self._lib.lsf_front_end_batch(self._ctx, ptr, n, H, W, W * 3, kind, int(stages), kk, C.byref(seg))
+        if rc == _lib.LSF_E_CAPACITY and seg.n_segments > self._cap and self._cap < self.max_output_rows:
+            # host buffers too small for this batch: grow them (the library reports the row count it needs) and run again;
+            # the carry of LSF_STAGE_MATCH_PREV is only advanced by a successful batch, so the retry matches the same frames
+            self._cap = min(self.max_output_rows, int(seg.n_segments * 1.25) + 64)
+            self._host = None
+            return self.process(frames, stages=stages, k=k)
         self._check(rc)
-        del dev_ptr
+        self._last_frames = dev_ptr      # device input stays alive for tap("image") until the next call
         self._last_n = n
         S = seg.n_segments
         if kk and kk != 8:
@@ -225,6 +237,14 @@ class FrontEnd:
         """AntiInstagramTransform update (line_detector_node.py:112-114); takes effect at the next batch."""
         sc = (C.c_float * 3)(*[float(x) for x in scale]); sf = (C.c_float * 3)(*[float(x) for x in shift])
         self._check(self._lib.lsf_set_color_transform(self._ctx, sc, sf))
+
+    def set_tie_order(self, tie_order):
+        """Order of equal-distance neighbours: TIES_REFERENCE (the reference's Mihasher order) or TIES_INDEX."""
+        self._check(self._lib.lsf_set_tie_order(self._ctx, int(tie_order)))
+
+    def cancel_prefetch(self):
+        """Drop batches staged by prefetch() that will not be consumed."""
+        self._check(self._lib.lsf_cancel_prefetch(self._ctx))
 
     def set_chunk_frames(self, chunk_frames):
         """Pipeline chunking of the next batches: 0 automatic, < 0 one stream (timings() then lists every kernel)."""

@@ -216,3 +216,11 @@ def front_end_frame(image, cfg, img_size, top_cutoff, camera, homography, scale=
         kls, d72, d32 = lbd(out["lines_px"], dx, dy)
         out.update(gray=gray, dx=dx, dy=dy, keylines=kls, desc72=d72, desc32=d32)
     return out
+
+
+def knn_mihasher(q, m, k):
+    """knnMatch in the reference's own (Mihasher) result order: distance, then hash-discovery order; D = 128."""
+    q = _u8(q).reshape(-1, 32); m = _u8(m).reshape(-1, 32)
+    idx = np.empty((len(q), k), np.int32); dist = np.empty((len(q), k), np.int32)
+    lib().orc_knn_mihasher(_p(q), len(q), _p(m), len(m), int(k), _p(idx), _p(dist))
+    return idx, dist

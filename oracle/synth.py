@@ -63,18 +63,20 @@ def frame(seed, H=480, W=640, dense=False):
     return cv2.add(img, noise)
 
 
-def sequence(n, base_seed=0, H=480, W=640, dense=False):
-    """n frames [n,H,W,3] following a smooth pose trajectory (frame t: seed = base_seed + t)."""
+def sequence(n, base_seed=0, H=480, W=640, dense=False, start=0):
+    """Frames start .. start+n-1 ([n,H,W,3]) of the sequence `base_seed`: one scene following a smooth pose trajectory
+    (frame t: noise seed = base_seed + t)."""
     scene = base_scene(H, W, dense=dense, seed=base_seed)
     out = np.empty((n, H, W, 3), np.uint8)
-    for t in range(n):
+    for i in range(n):
+        t = start + i
         rot = 12.0 * math.sin(2 * math.pi * t / 240.0)
         sc = 1.05 + 0.12 * math.sin(2 * math.pi * t / 173.0 + 0.7)
         tx = 0.04 * W * math.sin(2 * math.pi * t / 97.0)
         ty = 0.03 * H * math.cos(2 * math.pi * t / 131.0)
         img = _warp(scene, rot, sc, tx, ty)
         rng = np.random.default_rng(base_seed + t)
-        out[t] = cv2.add(img, rng.integers(0, 6, img.shape, dtype=np.uint8))
+        out[i] = cv2.add(img, rng.integers(0, 6, img.shape, dtype=np.uint8))
     return out
 
 

@@ -15,16 +15,22 @@ ENDPOINT_TOL_PX = 0.5      # north_star: segment endpoints within 0.5 px
 GROUND_TOL_M = 1e-4        # north_star: ground-projected points within 1e-4 m
 
 
-def _front_end(L, rg, isz, cut, H, W, n, **kw):
+def _front_end(L, rg, isz, cut, H, W, n, configuration=None, **kw):
     cam, Hg = (rg.DEFAULT_CAMERA, rg.DEFAULT_HOMOGRAPHY) if (W, H) == (640, 480) else rg.scaled_camera(W, H)
-    fe = L.FrontEnd(dict(L.DEFAULT_DETECTOR_CONFIGURATION), img_size=isz, top_cutoff=cut, camera=cam, homography=Hg,
-                    src_size=(H, W), max_batch=n, max_segments_per_frame=4096, **kw)
+    kw.setdefault("max_segments_per_frame", 4096)
+    fe = L.FrontEnd(dict(configuration or L.DEFAULT_DETECTOR_CONFIGURATION), img_size=isz, top_cutoff=cut, camera=cam, homography=Hg,
+                    src_size=(H, W), max_batch=n, **kw)
     return fe, cam, Hg
 
 
-def _check_batch(L, cm, rg, cfg, frames, isz, cut, scale=(1, 1, 1), shift=(0, 0, 0), describe=True, dense_maps=True):
+def _check_batch(L, cm, rg, cfg, frames, isz, cut, scale=(1, 1, 1), shift=(0, 0, 0), describe=True, dense_maps=True,
+                 configuration=None, golden=None):
+    """GPU (through the C ABI) vs the C oracle, stage by stage, EXACT: dense maps, counts, endpoints (float equality is
+    recorded, the 0.5 px bar asserted), ground points, keep mask, and every bit of every LBD descriptor.
+    configuration: raw detector dict for the GPU (cfg is its checked form for the oracle); golden(f) -> dict from
+    tests/realset.golden for frame f: the REFERENCE class's own output, compared exactly as well."""
     n, H, W = frames.shape[:3]
-    fe, cam, Hg = _front_end(L, rg, isz, cut, H, W, n, ai_scale=scale, ai_shift=shift)
+    fe, cam, Hg = _front_end(L, rg, isz, cut, H, W, n, configuration=configuration, ai_scale=scale, ai_shift=shift)
     stages = L.STAGE_DETECT | L.STAGE_GROUND | (L.STAGE_DESCRIBE if describe else 0)
     b = fe.process(frames, stages=stages)
     stats = dict(frames=n, exact_frames=0, max_endpoint_err=0.0, max_ground_err=0.0, desc_bits_bad=0, desc_bits=0)
@@ -58,10 +64,16 @@ def _check_batch(L, cm, rg, cfg, frames, isz, cut, scale=(1, 1, 1), shift=(0, 0,
             if describe:
                 assert np.array_equal(fe.tap("gray", f), o["gray"])
                 assert np.array_equal(fe.tap("dx", f), o["dx"]) and np.array_equal(fe.tap("dy", f), o["dy"])
-                stats["desc_bits_bad"] += int(np.unpackbits(g["desc"] ^ o["desc32"]).sum())
+                assert np.array_equal(g["desc"], o["desc32"]), "LBD descriptors differ (frame %d): %d bits" % (
+                    f, int(np.unpackbits(g["desc"] ^ o["desc32"]).sum()))
                 stats["desc_bits"] += g["desc"].size * 8
         else:
             stats["exact_frames"] += 1
+        if golden is not None:
+            gd = golden(f)
+            assert g["counts"] == gd["counts"], "counts differ from the reference class (frame %d)" % f
+            assert np.array_equal(g["lines_px"], gd["lines"]) and np.array_equal(g["normals"], gd["normals"])
+            assert np.array_equal(g["centers"], gd["centers"])
     fe.close()
     return stats
 
@@ -80,8 +92,61 @@ def test_native_640x480(mods):
     frames = np.stack([synth.frame(s) for s in range(24)])
     st = _check_batch(L, cm, rg, cfg, frames, (480, 640), 0)
     print(st)
+    assert st["exact_frames"] == st["frames"] and st["desc_bits"] > 0
+
+
+def test_real_images_native_vs_oracle_and_reference_class(mods):
+    """The reference's own camera frames (28 real 640x480 JPEGs, 4 237 segments) at native size: GPU == C oracle on every
+    stage and every descriptor bit, and == the Detections the UNMODIFIED reference class produced (tests/golden)."""
+    import realset
+    L, cm, rg, synth, cfg = mods
+    frames = np.stack([realset.image(i) for i in range(realset.count())])
+    st = _check_batch(L, cm, rg, cfg, frames, (480, 640), 0, golden=lambda f: realset.golden("n%d" % f))
+    print(st)
+    assert st["exact_frames"] == st["frames"] == realset.count()
+
+
+def test_real_images_default_geometry(mods):
+    """Same frames through the reference default geometry (nearest 160x120, top 40 rows cut)."""
+    import realset
+    L, cm, rg, synth, cfg = mods
+    frames = np.stack([realset.image(i) for i in range(realset.count())])
+    st = _check_batch(L, cm, rg, cfg, frames, (120, 160), 40, golden=lambda f: realset.golden("d%d" % f))
     assert st["exact_frames"] == st["frames"]
-    assert st["desc_bits_bad"] <= 1e-4 * st["desc_bits"]
+
+
+def test_shipped_yaml_threshold_sets(mods):
+    """Every distinct threshold set of the shipped line_detector_node/*.yaml (Canny 50/150 and 60/150, the other HSV
+    ranges): GPU == oracle == the reference class configured with that set."""
+    import realset
+    L, cm, rg, synth, cfg = mods
+    sets, idx = realset.yaml_sets()
+    frames = np.stack([realset.image(i) for i in idx])
+    for name, conf in sorted(sets.items()):
+        st = _check_batch(L, cm, rg, rg.check_configuration(dict(conf)), frames, (120, 160), 40, configuration=conf,
+                          golden=lambda f, name=name: realset.golden("y_%s_%d" % (name, idx[f])))
+        assert st["exact_frames"] == st["frames"], name
+        # and at native size against the oracle
+        st = _check_batch(L, cm, rg, rg.check_configuration(dict(conf)), frames[:3], (480, 640), 0, configuration=conf)
+        assert st["exact_frames"] == st["frames"], name
+
+
+def test_lbd_vs_compiled_reference_golden(mods):
+    """Descriptors of the GPU for the golden segment lists == the reference's compiled C++ (tests/golden/lbd_reference.npz)."""
+    import realset
+    L, cm, rg, synth, cfg = mods
+    g = np.load(realset.PATH.replace("real_images", "lbd_reference"))
+    for k, case in enumerate(g["cases"]):
+        kind, idx, H, W, dense = [int(v) for v in case]
+        img = synth.frame(idx, H, W, dense=bool(dense)) if kind == 0 else realset.image(idx)
+        fe, cam, Hg = _front_end(L, rg, (H, W), 0, H, W, 1)
+        b = fe.process(img, stages=L.STAGE_DETECT | L.STAGE_DESCRIBE)
+        assert np.array_equal(b.lines_px, g["%d_lines" % k])
+        assert np.array_equal(b.desc, g["%d_desc32" % k]), "case %d" % k
+        # the stand-alone describe entry on caller-supplied lines
+        d = fe.describe(g["%d_lines" % k], [0, len(b.lines_px)])
+        assert np.array_equal(d, g["%d_desc32" % k])
+        fe.close()
 
 
 def test_reference_default_resize_crop(mods):
@@ -130,9 +195,11 @@ def test_odd_sizes_and_ragged_words(mods):
 def test_1080p_dense_frame(mods):
     """configs[2] shape (1920x1080 dense): multi-strip hysteresis, large support-pixel lists."""
     L, cm, rg, synth, cfg = mods
-    frames = np.stack([synth.frame(s, 1080, 1920, dense=True) for s in range(2)])
-    st = _check_batch(L, cm, rg, cfg, frames, (1080, 1920), 0, describe=False)
+    frames = np.stack([synth.frame(s, 1080, 1920, dense=True) for s in range(8)])
+    st = _check_batch(L, cm, rg, cfg, frames, (1080, 1920), 0, describe=True, dense_maps=False)
     print(st)
+    assert st["exact_frames"] == st["frames"] and st["desc_bits"] > 8 * 1500 * 256
+    st = _check_batch(L, cm, rg, cfg, frames[:1], (1080, 1920), 0, describe=True, dense_maps=True)
     assert st["exact_frames"] == st["frames"]
 
 
@@ -196,10 +263,21 @@ def test_project_filter_given_oracle_endpoints(mods):
 
 
 def test_knn_hamming_exact_with_ties(mods):
-    """K13: indices bit-exact vs the oracle and cv2.BFMatcher; duplicated rows -> smallest index wins."""
+    """K13: indices bit-exact.  Reference order (default): vs the oracle's Mihasher-order model and the golden produced by the
+    reference's compiled BinaryDescriptorMatcher on a tie-heavy set.  Index order: vs the oracle and cv2.BFMatcher."""
+    import realset
     L, cm, rg, synth, cfg = mods
     q, m, src = synth.descriptor_sets(700, 30000, seed=3)
     fe = L.FrontEnd(max_batch=1)
+    g = np.load(realset.PATH.replace("real_images", "lbd_reference"))
+    for k in (1, 2, 4, 8):
+        idx, dist = fe.knn(g["knn_q"], g["knn_m"], k=k, max_dist=L.MATCH_RADIUS)
+        assert np.array_equal(idx, g["knn_idx_%d" % k]) and np.array_equal(dist, g["knn_dist_%d" % k]), k
+    for k in (1, 3, 5):
+        idx, dist = fe.knn(q, m, k=k, max_dist=L.MATCH_RADIUS)
+        oi, od = cm.knn_mihasher(q, m, k)
+        assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+    fe.set_tie_order(L.TIES_INDEX)
     for k in (1, 2, 5):
         idx, dist = fe.knn(q, m, k=k)
         oi, od = cm.knn_hamming(q, m, k)
@@ -243,7 +321,7 @@ def test_match_stage_frame_to_frame(mods):
     fe.map_clear(); fe.map_add(d0)
     assert fe.map_size() == len(d0)
     b1 = fe.process(frames[1:2], stages=L.STAGE_DETECT | L.STAGE_GROUND | L.STAGE_DESCRIBE | L.STAGE_MATCH, k=2)
-    oi, od = cm.knn_hamming(b1.desc, d0, 2)
+    oi, od = cm.knn_mihasher(b1.desc, d0, 2)
     assert np.array_equal(b1.match_idx, oi) and np.array_equal(b1.match_dist, od)
     fe.close()
 
@@ -325,8 +403,9 @@ def test_chunk_pipeline_and_prefetch_are_invisible(mods):
         o = cm.front_end_frame(frames[f], cfg, (480, 640), 0, cam, Hg, descriptors=True)
         g = b.frame(f)
         assert g["counts"] == o["counts"] and np.array_equal(g["keep"], o["keep"])
+        assert np.array_equal(g["desc"], o["desc32"])
         if prev is not None and len(prev) and len(g["desc"]):
-            oi, od = cm.knn_hamming(g["desc"], prev, 2)
+            oi, od = cm.knn_mihasher(g["desc"], prev, 2)
             s = b.frame_slice(f)
             assert np.array_equal(b.match_idx[s], oi) and np.array_equal(b.match_dist[s], od)
         prev = g["desc"].copy()
@@ -386,4 +465,109 @@ def test_lane_filter_votes(mods):
         want = rg.lane_filter_votes(g["ground"], g["color"])
         assert np.array_equal(hist[f], want), "frame %d" % f
         assert hist[f].sum() == int(g["keep"].sum())
+    fe.close()
+
+
+def test_global_used_bitmap_fallback(mods, monkeypatch):
+    """The USED bitmap of region growing normally lives in shared memory; frames too large for that use a per-image bitmap
+    in global memory shared by all tasks of the image.  LSF_FORCE_GLOBAL_USED takes that path at a size the oracle
+    checks quickly (dense frames: many tasks per image run concurrently)."""
+    L, cm, rg, synth, cfg = mods
+    monkeypatch.setenv("LSF_FORCE_GLOBAL_USED", "1")
+    frames = np.stack([synth.frame(s, dense=True) for s in range(4)] + [synth.frame(s) for s in range(4)])
+    for _ in range(2):
+        st = _check_batch(L, cm, rg, cfg, frames, (480, 640), 0, dense_maps=False)
+        assert st["exact_frames"] == st["frames"]
+
+
+def test_two_contexts_two_threads_and_concurrent_color_transform(mods):
+    """Several contexts in one process, driven from different threads (on two devices when the box has them): every one
+    gets its own constant tables / shared-memory opt-ins and its own launch counter.  lsf_set_color_transform from a second
+    thread during a batch: the batch uses either the old or the new transform, never a mix."""
+    import threading
+    import torch
+    L, cm, rg, synth, cfg = mods
+    frames = np.stack([synth.frame(s) for s in range(400, 406)])
+    ndev = torch.cuda.device_count()
+    ref = None
+    results, errors = {}, []
+
+    def work(tag, device):
+        try:
+            fe, cam, Hg = _front_end(L, rg, (480, 640), 0, 480, 640, len(frames), device=device)
+            out = []
+            for _ in range(3):
+                b = fe.process(frames, stages=L.STAGE_DETECT | L.STAGE_GROUND | L.STAGE_DESCRIBE)
+                out.append((b.counts.copy(), b.lines_px.copy(), b.desc.copy(), b.keep.copy()))
+            results[tag] = (out, fe.launch_count())
+            fe.close()
+        except Exception as e:       # surfaced in the main thread
+            errors.append((tag, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(t, t % ndev)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for tag, (out, launches) in results.items():
+        for o in out:
+            if ref is None:
+                ref = o
+            assert all(np.array_equal(a, b) for a, b in zip(ref, o)), "context %d differs" % tag
+        assert launches == results[0][1] > 0          # per-context launch counts
+    o = cm.front_end_frame(frames[0], cfg, (480, 640), 0, rg.DEFAULT_CAMERA, rg.DEFAULT_HOMOGRAPHY, descriptors=True)
+    assert ref[0][0].tolist() == o["counts"] and np.array_equal(ref[2][:sum(o["counts"])], o["desc32"])
+
+    # concurrent colour-transform updates
+    fe, cam, Hg = _front_end(L, rg, (480, 640), 0, 480, 640, len(frames))
+    A, B = ((1.0, 1.0, 1.0), (0.0, 0.0, 0.0)), ((1.1, 0.93, 1.27), (3.5, -7.25, 12.0))
+    want = []
+    for sc, sf in (A, B):
+        fe.set_color_transform(sc, sf)
+        b = fe.process(frames, stages=L.STAGE_DETECT)
+        want.append((b.counts.copy(), b.lines_px.copy()))
+    stop = threading.Event()
+
+    def flip():
+        i = 0
+        while not stop.is_set():
+            fe.set_color_transform(*(A, B)[i & 1])
+            i += 1
+
+    th = threading.Thread(target=flip)
+    th.start()
+    try:
+        for _ in range(20):
+            b = fe.process(frames, stages=L.STAGE_DETECT)
+            got = (b.counts.copy(), b.lines_px.copy())
+            assert any(np.array_equal(got[0], w[0]) and np.array_equal(got[1], w[1]) for w in want), "mixed colour transform"
+    finally:
+        stop.set()
+        th.join()
+    fe.close()
+
+
+def test_host_capacity_grows_and_stale_prefetch_is_dropped(mods):
+    """A dense frame with more segments than the host buffers were sized for is returned in full (buffers grow, like the
+    reference's detector returns however many lines it finds); a staged batch that is never consumed does not leak into a
+    later call that reuses the same pinned buffer with other contents."""
+    import torch
+    L, cm, rg, synth, cfg = mods
+    dense = synth.frame(1, dense=True)
+    fe, cam, Hg = _front_end(L, rg, (480, 640), 0, 480, 640, 2, max_segments_per_frame=16)
+    b = fe.process(dense, stages=L.STAGE_DETECT)
+    o = cm.front_end_frame(dense, cfg, (480, 640), 0, cam, Hg)
+    assert b.counts[0].tolist() == o["counts"] and b.n_segments == sum(o["counts"]) > 16
+    assert np.array_equal(b.lines_px, o["lines_px"])
+    buf = torch.from_numpy(np.stack([synth.frame(10), synth.frame(11)])).pin_memory().numpy()
+    want0 = fe.process(buf.copy(), stages=L.STAGE_DETECT).lines_px.copy()
+    fe.prefetch(buf)                                  # staged, then abandoned ...
+    other = np.stack([synth.frame(12), synth.frame(13)])
+    fe.process(other, stages=L.STAGE_DETECT)          # ... a non-matching host call drops it
+    buf[:] = other                                    # same pinned buffer, new contents
+    got = fe.process(buf, stages=L.STAGE_DETECT).lines_px.copy()
+    want1 = fe.process(other.copy(), stages=L.STAGE_DETECT).lines_px.copy()
+    assert np.array_equal(got, want1) and not np.array_equal(got, want0)
+    fe.prefetch(buf); fe.cancel_prefetch()
     fe.close()

@@ -174,3 +174,118 @@ def test_golden_lane_filter_votes():
         assert np.array_equal(counts / counts.sum(), ml)
         # the votes are exactly the segments line_sanity keeps
         assert counts.sum() == rg.sanity_keep(g["ground_%d" % k], g["color_%d" % k]).sum()
+
+
+# ---- real camera frames (tests/golden/real_images.npz: the reference's own JPEGs through the reference's own class) ----
+import realset  # noqa: E402
+
+
+def _check_against_golden(o, gd, det=None):
+    assert o["counts"] == gd["counts"]
+    assert np.array_equal(o["lines_px"], gd["lines"]) and np.array_equal(o["normal64"], gd["normals"])
+    assert np.array_equal(o["centers"], gd["centers"])
+    for ci, c in enumerate(realset.COLORS):
+        packed = np.packbits(o["bw"][ci] > 0)
+        if c + "_area" in gd:
+            assert np.array_equal(packed, gd[c + "_area"])
+        else:
+            assert realset.crc(packed) == gd[c + "_area_crc"]
+    packed = np.packbits(o["edges"] > 0)
+    if "edges" in gd:
+        assert np.array_equal(packed, gd["edges"])
+    else:
+        assert realset.crc(packed) == gd["edges_crc"]
+
+
+def test_golden_real_images_cmodel_native_and_default_geometry():
+    """28 real 640x480 frames of the reference repo: the C model reproduces the reference class's Detections exactly
+    (segment order, endpoints, normals, centres, area masks, Canny map) at 640x480 and at 160x120 cut 40."""
+    nseg = 0
+    for i in range(realset.count()):
+        img = realset.image(i)
+        for pre, isz, cut in (("n%d" % i, (480, 640), 0), ("d%d" % i, (120, 160), 40)):
+            o = cm.front_end_frame(img, CFG, isz, cut, rg.DEFAULT_CAMERA, rg.DEFAULT_HOMOGRAPHY)
+            _check_against_golden(o, realset.golden(pre))
+            nseg += sum(o["counts"])
+    assert nseg > 4000
+
+
+def test_golden_real_images_glue():
+    det = rg.LineDetectorLSD(dict(rg.DEFAULT_DETECTOR_CONFIG))
+    gp = rg.GroundProjection()
+    for i in range(0, realset.count(), 3):
+        r = rg.front_end_frame(realset.image(i), det, gp, (120, 160), 40)
+        gd = realset.golden("d%d" % i)
+        assert r["counts"] == gd["counts"] and np.array_equal(r["lines_px"], gd["lines"])
+
+
+def test_golden_yaml_threshold_sets():
+    """Every distinct threshold set of the shipped line_detector_node/*.yaml files (canny 50/150, 60/150, the other HSV
+    ranges): C model == the reference class run with that configuration."""
+    sets, frames = realset.yaml_sets()
+    assert {"bad_lighting", "universal", "226-night"} <= set(sets)
+    for name, conf in sets.items():
+        cfg = rg.check_configuration(dict(conf))
+        for i in frames:
+            o = cm.front_end_frame(realset.image(i), cfg, (120, 160), 40, rg.DEFAULT_CAMERA, rg.DEFAULT_HOMOGRAPHY)
+            _check_against_golden(o, realset.golden("y_%s_%d" % (name, i)))
+
+
+# ---- LBD / KeyLine / matcher: pinned to the reference's own compiled code (oracle/_ref via tests/golden/make_golden_lbd.py) ----
+LBD_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lbd_reference.npz")
+
+
+def _lbd_case_image(case):
+    kind, idx, H, W, dense = [int(v) for v in case]
+    return synth.frame(idx, H, W, dense=bool(dense)) if kind == 0 else realset.image(idx)
+
+
+def test_golden_lbd_keylines_and_descriptors_vs_compiled_reference():
+    """KeyLine fill (LSDDetector_custom.cpp:130-215) and computeLBD (binary_descriptor_custom.cpp:1026-1372) of the C model
+    equal the outputs of the reference's compiled C++: every KeyLine field, all 72 floats and all 256 bits, exactly."""
+    g = np.load(LBD_GOLD)
+    nl = 0
+    for k, case in enumerate(g["cases"]):
+        img = _lbd_case_image(case)
+        gray = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
+        blur, dx, dy = cm.gauss5_sobel(gray)
+        kl, d72, d32 = cm.lbd(g["%d_lines" % k], dx, dy)
+        ref = g["%d_keylines" % k]     # startX, startY, endX, endY, lineLength, numOfPixels, angle, response, size, class_id
+        assert np.array_equal(kl[:, :5], ref[:, :5]) and np.array_equal(kl[:, 6], ref[:, 5])
+        assert np.array_equal(kl[:, 5], ref[:, 6]) and np.array_equal(kl[:, 7], ref[:, 7])
+        assert np.array_equal(d32, g["%d_desc32" % k])
+        assert np.array_equal(d72, g["%d_desc72" % k])
+        nl += len(d32)
+    assert nl >= 2000
+
+
+def test_golden_knn_reference_order():
+    """orc_knn_mihasher == BinaryDescriptorMatcher::knnMatch of the compiled reference (indices AND order inside equal
+    distances) on a tie-heavy set; the smallest-index rule (cv2.BFMatcher) differs there, distances never do."""
+    g = np.load(LBD_GOLD)
+    q, m = g["knn_q"], g["knn_m"]
+    differs = 0
+    for k in (1, 2, 4, 8):
+        i, d = cm.knn_mihasher(q, m, k)
+        assert np.array_equal(i, g["knn_idx_%d" % k]) and np.array_equal(d, g["knn_dist_%d" % k])
+        bi, bd = cm.knn_hamming(q, m, k, 128)
+        assert np.array_equal(bd, d)
+        differs += int((bi != i).sum())
+    assert differs > 0      # the set really exercises the tie rule
+
+
+def test_live_compiled_reference_when_present():
+    """Where oracle/_ref exists (authoring container, or the prebuilt library that travels to the GPU box): fresh frames,
+    C model vs the reference's compiled code."""
+    from oracle import refnative as rn
+    if not rn.available():
+        pytest.skip("oracle/_ref not built here")
+    for seed in (31, 32):
+        o = cm.front_end_frame(synth.frame(seed), CFG, (480, 640), 0, rg.DEFAULT_CAMERA, rg.DEFAULT_HOMOGRAPHY, descriptors=True)
+        kl, d72, d32 = rn.keylines_lbd(o["gray"], o["lines_px"])
+        assert np.array_equal(d32, o["desc32"]) and np.array_equal(d72, o["desc72"])
+    q, m, _ = synth.descriptor_sets(100, 3000, seed=9)
+    for k in (1, 3):
+        ri, rd = rn.knn_match(q, m, k)
+        oi, od = cm.knn_mihasher(q, m, k)
+        assert np.array_equal(ri, oi) and np.array_equal(rd, od)
