@@ -135,7 +135,10 @@ void launch_seg_offsets(const Dims &d, Buffers &b, cudaStream_t st);
 void launch_segments(const Dims &d, const CamParams &cam, Buffers &b, int do_ground, cudaStream_t st);
 void launch_lane_votes(const CamParams &cam, int nseg, double delta_d, double delta_phi, int nd, int nphi, const Buffers &b, int *hist,
                        cudaStream_t st);
-void launch_pack_kept(int nseg, int frame_base, const Buffers &b, u8 *rec, int *count, cudaStream_t st);
+void launch_pack_kept(int nseg, int frame_base, const Buffers &b, u8 *rec, int cap, int *count, cudaStream_t st);
+void launch_gather_compact(const u8 *slots, size_t slot_bytes, int world, int cap, u8 *out, int *meta, cudaStream_t st);
+void launch_map_append(const u8 *rec, int n, const double *pose4, int pose_base, int n_pose, int map_n, double *m_ground, u8 *m_color,
+                       int *m_frame, u8 *m_desc, cudaStream_t st);
 void launch_gray_sobel(const Dims &d, const u8 *gray, short *dx, short *dy, cudaStream_t st);
 void launch_lbd(const Dims &d, const float *lines, const int *frame_of_seg, int nseg_cap, const int *seg_lo_dev,
                 const int *seg_hi_dev, const short *dx, const short *dy, u8 *desc, int *cursor, cudaStream_t st);

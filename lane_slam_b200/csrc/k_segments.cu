@@ -209,7 +209,7 @@ void launch_segments(const Dims &d, const CamParams &cam, Buffers &b, int do_gro
 // ---- kept segments -> 72-byte exchange records (single CTA: scan of the keep flags, then scatter) ----
 __global__ void __launch_bounds__(1024) k_pack_kept(int nseg, int frame_base, const u8 *__restrict__ keep, const int *__restrict__ frame,
                                                    const u8 *__restrict__ color, const double *__restrict__ ground,
-                                                   const u8 *__restrict__ desc, u8 *__restrict__ rec, int *__restrict__ count)
+                                                   const u8 *__restrict__ desc, u8 *__restrict__ rec, int cap, int *__restrict__ count)
 {
     __shared__ int wtot[32];
     __shared__ int carry;
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(1024) k_pack_kept(int nseg, int frame_base, co
         int woff = 0;
         for (int k = 0; k < warp; ++k) woff += wtot[k];
         const int excl = carry + woff + incl - v;
-        if (v) {
+        if (v && excl < cap) {      // records past the capacity are dropped; *count still reports how many there were
             u8 *r = rec + (size_t)excl * 72;
             *reinterpret_cast<int *>(r) = frame[i] + frame_base;
             *reinterpret_cast<u32 *>(r + 4) = (u32)color[i];
@@ -251,9 +251,86 @@ __global__ void __launch_bounds__(1024) k_pack_kept(int nseg, int frame_base, co
     if (tid == 0) *count = carry;
 }
 
-void launch_pack_kept(int nseg, int frame_base, const Buffers &b, u8 *rec, int *count, cudaStream_t st)
+void launch_pack_kept(int nseg, int frame_base, const Buffers &b, u8 *rec, int cap, int *count, cudaStream_t st)
 {
-    k_pack_kept<<<1, 1024, 0, st>>>(nseg, frame_base, b.o_keep, b.o_frame, b.o_color, b.o_ground, b.o_desc, rec, count);
+    k_pack_kept<<<1, 1024, 0, st>>>(nseg, frame_base, b.o_keep, b.o_frame, b.o_color, b.o_ground, b.o_desc, rec, cap, count);
+    ++g_launches;
+}
+
+// ---- exchange step, after the all-gather: [world] slots of { int count; pad to 16 B; cap x 72-byte records } ->
+// one contiguous record array in rank order (= global frame order for contiguous shards) + counts[world], total ----
+__global__ void __launch_bounds__(256) k_gather_compact(const u8 *__restrict__ slots, size_t slot_bytes, int world, int cap,
+                                                       u8 *__restrict__ out, int *__restrict__ meta /* [world + 2]: counts, total, overflow */)
+{
+    __shared__ int s_off[65];
+    if (threadIdx.x == 0) {
+        int run = 0, over = 0;
+        for (int r = 0; r < world; ++r) {
+            int c = *reinterpret_cast<const int *>(slots + (size_t)r * slot_bytes);
+            if (c > cap) { over = max(over, c); c = cap; }
+            s_off[r] = run;
+            run += c;
+        }
+        s_off[world] = run;
+        if (blockIdx.x == 0) {
+            for (int r = 0; r < world; ++r) meta[r] = s_off[r + 1] - s_off[r];
+            meta[world] = run; meta[world + 1] = over;
+        }
+    }
+    __syncthreads();
+    // 72-byte records = 18 words; grid-stride over all words of all ranks
+    for (int r = 0; r < world; ++r) {
+        const u32 *src = reinterpret_cast<const u32 *>(slots + (size_t)r * slot_bytes + 16);
+        u32 *dst = reinterpret_cast<u32 *>(out + (size_t)s_off[r] * 72);
+        const size_t nw = (size_t)(s_off[r + 1] - s_off[r]) * 18;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+    }
+}
+
+void launch_gather_compact(const u8 *slots, size_t slot_bytes, int world, int cap, u8 *out, int *meta, cudaStream_t st)
+{
+    k_gather_compact<<<148, 256, 0, st>>>(slots, slot_bytes, world, cap, out, meta);
+    ++g_launches;
+}
+
+// ---- map accumulation (what show_map + TF do, src/show_map/src/show_map.py:28-43, src/odometry/src/odometry.py:110-120):
+// every record's ground segment, expressed in the robot frame ("duck") of ITS frame, is moved to the map frame with that
+// frame's pose  p_map = R(theta) p + (x, y)  and appended to the device-resident map together with colour, frame id and
+// descriptor.  cos / sin of theta come from the host (pose[f] = {x, y, cos, sin}): the host's libm is the reference's. ----
+__global__ void __launch_bounds__(256) k_map_append(const u8 *__restrict__ rec, int n, const double4 *__restrict__ pose, int pose_base,
+                                                   int n_pose, int map_n, double *__restrict__ m_ground, u8 *__restrict__ m_color,
+                                                   int *__restrict__ m_frame, u8 *__restrict__ m_desc)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u8 *r = rec + (size_t)i * 72;
+    const int frame = *reinterpret_cast<const int *>(r);
+    const double *g = reinterpret_cast<const double *>(r + 8);
+    double x1 = g[0], y1 = g[1], x2 = g[2], y2 = g[3];
+    const int pf = frame - pose_base;
+    if (pose && pf >= 0 && pf < n_pose) {
+        const double4 p = pose[pf];
+        const double ax = __dadd_rn(__dsub_rn(__dmul_rn(p.z, x1), __dmul_rn(p.w, y1)), p.x);
+        const double ay = __dadd_rn(__dadd_rn(__dmul_rn(p.w, x1), __dmul_rn(p.z, y1)), p.y);
+        const double bx = __dadd_rn(__dsub_rn(__dmul_rn(p.z, x2), __dmul_rn(p.w, y2)), p.x);
+        const double by = __dadd_rn(__dadd_rn(__dmul_rn(p.w, x2), __dmul_rn(p.z, y2)), p.y);
+        x1 = ax; y1 = ay; x2 = bx; y2 = by;
+    }
+    const size_t o = (size_t)map_n + i;
+    m_ground[4 * o] = x1; m_ground[4 * o + 1] = y1; m_ground[4 * o + 2] = x2; m_ground[4 * o + 3] = y2;
+    m_color[o] = r[4];
+    m_frame[o] = frame;
+    const uint2 *d = reinterpret_cast<const uint2 *>(r + 40);
+    uint2 *md = reinterpret_cast<uint2 *>(m_desc + o * 32);
+    md[0] = d[0]; md[1] = d[1]; md[2] = d[2]; md[3] = d[3];
+}
+
+void launch_map_append(const u8 *rec, int n, const double *pose4, int pose_base, int n_pose, int map_n, double *m_ground, u8 *m_color,
+                       int *m_frame, u8 *m_desc, cudaStream_t st)
+{
+    if (n <= 0) return;
+    k_map_append<<<(n + 255) / 256, 256, 0, st>>>(rec, n, reinterpret_cast<const double4 *>(pose4), pose_base, n_pose, map_n, m_ground,
+                                                   m_color, m_frame, m_desc);
     ++g_launches;
 }
 
