@@ -45,6 +45,7 @@ ALGO_BYTES = {
 
 # DRAM traffic per frame (dram__bytes_read.sum + dram__bytes_write.sum) of the dense kernels, from the ncu --set full
 # capture profiles/r01f_ncu_full_296frames.csv (296 frames per launch, divided by 296)
+TRAFFIC_SOURCE = "ncu --set full, profiles/r01f_ncu_full_296frames.csv, scaled from 296 to %d frames"
 TRAFFIC_BYTES = {
     "color_canny": (272.836e6 + 151.673e6) / 296,
     "hysteresis_dilate": (56.880e6 + 28.300e6) / 296,
@@ -126,9 +127,18 @@ def bind_to_gpu_numa_node(torch, local):
         print("[bench] NUMA binding skipped: %r" % (e,), file=sys.stderr, flush=True)
 
 
-def make_frames(n, base_seed):
+def make_frames(n, base_seed, start=0, h=H, w=W, dense=False):
     from oracle import synth  # input generator only (test/bench infrastructure)
-    return synth.sequence(n, base_seed=base_seed, H=H, W=W)
+    return synth.sequence(n, base_seed=base_seed, H=h, W=w, dense=dense, start=start)
+
+
+def workload_config(frames_per_gpu):
+    """The `config` object of the JSON line: identical for the GPU arm and the reference (CPU) arm -- same generator, same
+    seeds (rank r replays synth.sequence(base_seed = r * frames_per_gpu)), same detector configuration and stages."""
+    return {"workload": WORKLOAD, "frames_per_step_per_gpu": frames_per_gpu, "img_size": [H, W], "top_cutoff": 0, "k": K_NN,
+            "detector": "line_detector_node/default.yaml thresholds", "stages": "detect+ground+sanity+describe+match_prev",
+            "input": "synth.sequence(base_seed = rank * frames_per_step_per_gpu), uint8 BGR", "match_radius": 128,
+            "l2": "inputs 921.6 MB per step exceed the 126 MB L2 (no flush needed)"}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -138,8 +148,8 @@ def _cpu_worker(args):
     import cv2
     cv2.setNumThreads(1)
     from oracle import cmodel as cm, reference_glue as rg
-    seed0, count = args
-    frames = make_frames(count, seed0)
+    start, count = args
+    frames = make_frames(count, 0, start=start)          # frames [start, start + count) of rank 0's sequence
     det = rg.LineDetectorLSD(dict(rg.DEFAULT_DETECTOR_CONFIG))
     gp = rg.GroundProjection()
     prev = None
@@ -153,7 +163,7 @@ def _cpu_worker(args):
         dy = cv2.Sobel(blur, cv2.CV_16S, 0, 1, ksize=3)
         desc = cm.lbd(r["lines_px"], dx, dy)[2] if len(r["lines_px"]) else np.zeros((0, 32), np.uint8)
         if prev is not None and len(prev) and len(desc):
-            rg.knn_hamming_bf(desc, prev, min(K_NN, len(prev)))
+            rg.knn_hamming_bf(desc, prev, min(K_NN, len(prev)))     # cv2.BFMatcher: all the matching work, vectorised
         prev = desc
         nseg += len(desc)
     return time.perf_counter() - t0, count, nseg
@@ -163,7 +173,8 @@ def cpu_baseline(sample_frames, cores):
     """Frames/s of the CPU path with `cores` single-threaded workers, on `sample_frames` frames of the workload."""
     import multiprocessing as mp
     per = max(1, sample_frames // cores)
-    jobs = [(1000 + i * per, per) for i in range(cores)]
+    # contiguous pieces spread over the 1000-frame sequence the GPU arm replays (same seeds, same arrays)
+    jobs = [((i * N_FRAMES) // cores, per) for i in range(cores)]
     ctx = mp.get_context("spawn")     # never fork a process that may hold CUDA / OpenMP state
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
@@ -191,10 +202,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / fps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": total, "img_size": [H, W], "top_cutoff": 0, "k": K_NN},
+        "config": workload_config(args.frames),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": "%d frames of the workload per step, %d single-threaded cv2 workers "
-                                   "(restated reference glue + cv2 4.13 LSD/Canny, C LBD, cv2.BFMatcher)" % (total, cores)},
+                         "sample": "%d frames per step = %d contiguous pieces of the same 1000-frame sequence (same seeds), one "
+                                   "single-threaded cv2 worker per core (restated reference glue + cv2 4.13 LSD/Canny, C LBD, "
+                                   "cv2.BFMatcher)" % (total, cores)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -204,9 +216,52 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
+def parity_gate(L, b, frames_np, n_check=64):
+    """BASELINE.md 3 / SURVEY 8d: the parity gate on the BENCHMARKED data.  n_check frames spread over the step are redone by the
+    CPU oracle (oracle/: test infrastructure, used here only as the checker, outside every timed region) and compared with
+    what the timed GPU step returned: segment counts per colour, endpoints, ground points, sanity keep mask, every bit of every
+    descriptor and the frame-to-frame match indices given identical descriptors."""
+    from oracle import cmodel as cm, reference_glue as rg
+    cfg = rg.check_configuration(dict(rg.DEFAULT_DETECTOR_CONFIG))
+    n = len(frames_np)
+    idx = sorted(set(np.linspace(1, n - 1, n_check).round().astype(int).tolist()))
+    st = dict(frames=len(idx), exact_frames=0, count_mismatch_frames=0, max_endpoint_px=0.0, max_ground_m=0.0, desc_bits_bad=0,
+              desc_bits=0, match_rows_bad=0, match_rows=0, segments=0)
+    for f in idx:
+        o = cm.front_end_frame(frames_np[f], cfg, (H, W), 0, rg.DEFAULT_CAMERA, rg.DEFAULT_HOMOGRAPHY, descriptors=True)
+        g = b.frame(f)
+        ok = g["counts"] == o["counts"]
+        if not ok:
+            st["count_mismatch_frames"] += 1
+            continue
+        S = len(o["lines_px"])
+        st["segments"] += S
+        if S:
+            st["max_endpoint_px"] = max(st["max_endpoint_px"], float(np.abs(g["lines_px"] - o["lines_px"]).max()))
+            fin = np.isfinite(o["ground"]) & np.isfinite(g["ground"])
+            if fin.any():
+                st["max_ground_m"] = max(st["max_ground_m"], float(np.abs(g["ground"][fin] - o["ground"][fin]).max()))
+            bad_bits = int(np.unpackbits(g["desc"] ^ o["desc32"]).sum())
+            st["desc_bits_bad"] += bad_bits; st["desc_bits"] += S * 256
+            ok = ok and np.array_equal(g["keep"], o["keep"]) and bad_bits == 0 and st["max_endpoint_px"] <= 0.5 and st["max_ground_m"] <= 1e-4
+            prev = b.frame(f - 1)["desc"]
+            if len(prev):
+                oi, od = cm.knn_mihasher(o["desc32"], prev, K_NN)       # the reference's own result order (Mihasher), radius 128
+                sl = b.frame_slice(f)
+                bad_rows = int((b.match_idx[sl] != oi).any(axis=1).sum() + 0)
+                st["match_rows_bad"] += bad_rows; st["match_rows"] += S
+                ok = ok and bad_rows == 0 and np.array_equal(b.match_dist[sl], od)
+        st["exact_frames"] += bool(ok)
+    st["pass_fraction"] = st["exact_frames"] / max(1, st["frames"])
+    st["gate"] = ">= 0.95 of frames: counts / keep / descriptor bits / match indices exact, endpoints <= 0.5 px, ground <= 1e-4 m"
+    st["checker"] = "oracle/csrc/lane_oracle.c (pinned to the reference class, cv2 4.13 and the reference's compiled line_descriptor)"
+    return st
+
+
 def run_gpu(args):
     import torch
     import lane_slam_b200 as L
+    from lane_slam_b200 import odometry
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -215,7 +270,6 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     if world > 1:
         bind_to_gpu_numa_node(torch, local)
-    if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = args.frames
@@ -232,14 +286,28 @@ def run_gpu(args):
     fe = L.FrontEnd(dict(L.DEFAULT_DETECTOR_CONFIGURATION), img_size=(H, W), top_cutoff=0, src_size=(H, W), max_batch=n,
                     device=local, max_segments_per_frame=256, pinned=True)
     stages = L.STAGE_DETECT | L.STAGE_GROUND | L.STAGE_DESCRIBE | L.STAGE_MATCH_PREV
-    from lane_slam_b200 import dist as ldist
+    # the path's one exchange step lives in liblsf.so: one ncclAllGather on the ctx's exchange stream, overlapped with the next step
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if world > 1:
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(odometry.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+    fe.exchange_init(rank=rank, world=world, unique_id=bytes(uid.cpu().numpy()) if world > 1 else None)
+    inflight = [0]
+    kept_seen = [0]
 
     def step(frames):
         fe.reset_sequence()
         b = fe.process(frames, stages=stages, k=K_NN)
         if world > 1:
-            ldist.allgather_kept_device(fe, frame_base=rank * n, device=torch.device("cuda", local))   # the path's one exchange step
+            if inflight[0]:                                   # the exchange of the previous step ran under this step's kernels
+                _, ntot, _ = fe.exchange_wait(); inflight[0] -= 1; kept_seen[0] = ntot
+            fe.allgather_start(frame_base=rank * n); inflight[0] += 1
         return b
+
+    def drain():
+        while inflight[0]:
+            _, ntot, _ = fe.exchange_wait(); inflight[0] -= 1; kept_seen[0] = ntot
 
     def barrier():
         if world > 1:
@@ -253,6 +321,7 @@ def run_gpu(args):
         stream the kernels are launched on (the lsf ctx stream); per-stage times come from the library's own
         events on the same stream.  stream_ahead: host frames are staged one step ahead with fe.prefetch() -- every
         step's host->device copy is still issued inside the timed region (the first one before the first step).
+        The last step's exchange is finished (lsf_exchange_wait orders the ctx stream behind it) before the closing event.
         Returns (seconds, per-stage ms, d2h bytes, last batch)."""
         stage_ms = {}
         d2h = 0
@@ -269,6 +338,7 @@ def run_gpu(args):
                 stage_ms[name] = stage_ms.get(name, 0.0) + ms
             S = b.n_segments
             d2h = S * (1 + 16 + 16 + 8 + 16 + 8 + 32 + 1 + 32 + 8 * K_NN) + (4 * n + 1) * 4
+        drain()
         e1.record(ext)
         barrier()
         e1.synchronize()
@@ -281,6 +351,7 @@ def run_gpu(args):
         b = step(dev)
         log("warmup %d: S=%d %s" % (i, b.n_segments, ["%s=%.2f" % x for x in fe.timings()]))
     step(pinned.numpy())
+    drain()
     log("warmup host path done")
     sampler = ClockSampler(local)
     if rank == 0:
@@ -288,6 +359,8 @@ def run_gpu(args):
     l0 = fe.launch_count()
     dt_dev, _, _, b = timed(dev, args.steps)
     launches = fe.launch_count() - l0
+    parity = parity_gate(L, b, frames_np, args.parity_frames) if (rank == 0 and args.parity_frames > 0) else None
+    seg_per_step, kept_per_step = int(b.n_segments), int(b.keep.sum())
     dt_e2e, _, d2h_bytes, b = timed(pinned.numpy(), args.steps, stream_ahead=True)
     dt_e2e_single, _, _, _ = timed(pinned.numpy(), args.steps)
     # per-kernel times for the roofline: same steps on ONE stream (chunk pipeline off) so that the library's
@@ -312,6 +385,17 @@ def run_gpu(args):
         ts = np.array(ts[30:]) * 1e3
         lat = {"batch1_p50_ms": float(np.percentile(ts, 50)), "batch1_p95_ms": float(np.percentile(ts, 95)), "frames": int(len(ts)),
                "how": "host wall clock around FrontEnd.process of one pinned host frame (all stages, k=2), after 30 warm-up frames"}
+    extra = {}
+    if "c5" in args.extras:
+        extra["c5"] = bench_c5(torch, dist, L, fe, dev, n, rank, world, local, args, log)
+    fe.close()
+    del dev
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1:
+        if "c4" in args.extras:
+            extra["c4"] = bench_c4(torch, L, local, log)
+        if "c3" in args.extras:
+            extra["c3"] = bench_c3(torch, L, local, args, log)
     if world > 1:
         t = torch.tensor([dt_dev, dt_e2e, dt_e2e_single], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -343,15 +427,18 @@ def run_gpu(args):
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": dom["frac"], "traffic": dom["dram_traffic_bytes_per_launch"],
                 "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_frame"] * n, "peak_source": peak_src,
-                "traffic_source": "ncu --set full, profiles/r01f_ncu_full_296frames.csv, scaled from 296 to %d frames" % n,
+                "traffic_source": TRAFFIC_SOURCE % n,
                 "note": "dominant HBM-bound kernel; the LSD search (lsd_core) is latency-bound, see 'kernels'"}
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": 1e3 * dt_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": n, "pipeline": "device frames: 2 chunks, host frames: 8 chunks over 8 streams (copy of chunk c+1 overlaps kernels of chunk c)", "img_size": [H, W], "top_cutoff": 0, "k": K_NN,
-                   "l2": "inputs 921.6 MB per step exceed the 126 MB L2 (no flush needed)",
-                   "segments_per_step": int(b.n_segments), "kept_per_step": int(b.keep.sum())},
+        "config": workload_config(n),
+        "pipeline": {"chunks": "device frames: 2 chunks, host frames: 8 chunks over 8 streams (copy of chunk c+1 overlaps kernels of chunk c)",
+                     "segments_per_step": seg_per_step, "kept_per_step": kept_per_step,
+                     "exchange": None if world == 1 else "lsf_allgather_segments: one ncclAllGather of fixed-capacity slots on the ctx's exchange "
+                                                        "stream, started after step i and finished under step i+1 (last one inside the timed region); "
+                                                        "%d records gathered per step" % kept_seen[0]},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(n * H * W * 3), "d2h_bytes_per_step": int(d2h_bytes),
                 "ms_per_step": 1e3 * dt_e2e / args.steps,
                 "how": "host (pinned) frames through FrontEnd.process; input staging is double-buffered: fe.prefetch() starts the "
@@ -361,7 +448,7 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "latency": dict(lat, batch1000_ms_per_frame_amortised=1e3 * dt_dev / args.steps / n,
                         batch1000_step_ms=1e3 * dt_dev / args.steps) if lat else None,
-        "roofline": roofline, "kernels": kernels, "clocks": clocks,
+        "roofline": roofline, "kernels": kernels, "clocks": clocks, "parity": parity, "extra_configs": extra,
     }
     if world == 1 and not args.no_cpu:
         # the CPU leg runs in a fresh interpreter (no CUDA state), bounded in time
@@ -376,6 +463,122 @@ def run_gpu(args):
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations, measured after the headline (CUDA events on the ctx stream)
+# ------------------------------------------------------------------------------------------------------
+def _event_ms(torch, fe, local, fn, reps):
+    ext = torch.cuda.ExternalStream(fe.stream(), device=torch.device("cuda", local))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(ext)
+    for _ in range(reps):
+        out = fn()
+    e1.record(ext)
+    e1.synchronize()
+    return e0.elapsed_time(e1) / reps, out
+
+
+def bench_c3(torch, L, local, args, log):
+    """configs[2]: batch-256 1920x1080 dense lane frames, detection + descriptors (+ ground / sanity)."""
+    from oracle import synth
+    nb, h, w = args.c3_batch, 1080, 1920
+    pool = np.stack([synth.frame(s, h, w, dense=True) for s in range(8)])
+    frames = torch.from_numpy(pool[np.arange(nb) % len(pool)].copy()).cuda()
+    cam, Hg = L.scaled_calibration(w, h)
+    fe = L.FrontEnd(dict(L.DEFAULT_DETECTOR_CONFIGURATION), img_size=(h, w), top_cutoff=0, camera=cam, homography=Hg, src_size=(h, w),
+                    max_batch=nb, device=local, max_segments_per_frame=4096, pinned=True)
+    st = L.STAGE_DETECT | L.STAGE_GROUND | L.STAGE_DESCRIBE
+    b = fe.process(frames, stages=st)
+    b = fe.process(frames, stages=st)
+    ms, b = _event_ms(torch, fe, local, lambda: fe.process(frames, stages=st), 2)
+    fe.set_chunk_frames(-1)
+    fe.process(frames, stages=st)
+    kern = {k: round(v, 3) for k, v in fe.timings()}
+    out = {"workload": "batch-%d 1920x1080 dense synthetic lane frames: detect + ground/sanity + LBD descriptors" % nb, "batch": nb,
+           "frames_per_s": nb / (ms * 1e-3), "ms_per_batch": ms, "segments_per_frame": b.n_segments / nb,
+           "distinct_frames": len(pool), "input": "resident in HBM (%.2f GB > L2)" % (nb * h * w * 3 / 1e9),
+           "algorithmic_GBps_21.7N_model": 21.7 * h * w * nb / (ms * 1e-3) / 1e9, "kernels_ms_single_stream": kern}
+    fe.close()
+    log("c3 done: %s" % out)
+    return out
+
+
+def bench_c4(torch, L, local, log):
+    """configs[3]: line_associator Hamming kNN, 2 000 query segments vs 100 000 accumulated map lines (256-bit codes), k = 2."""
+    from oracle import synth
+    q, m, src = synth.descriptor_sets(2000, 100000, seed=0)
+    fe = L.FrontEnd(max_batch=1, device=local)
+    dq, dm = torch.from_numpy(q).cuda(), torch.from_numpy(m).cuda()
+    di = torch.empty((2000, 2), dtype=torch.int32, device="cuda"); dd = torch.empty_like(di)
+    call = lambda: fe.knn_device(dq.data_ptr(), 2000, dm.data_ptr(), 100000, 2, di.data_ptr(), dd.data_ptr(), max_dist=L.MATCH_RADIUS)
+    for _ in range(5):
+        call()
+    ms, _ = _event_ms(torch, fe, local, call, 50)
+    kms = dict(fe.timings()).get("knn", None)
+    ok = bool((di[:, 0].cpu().numpy() == np.where(src >= 100000 - 64, src - (100000 - 64), src)).all())
+    pairs = 2000 * 100000
+    out = {"workload": "Hamming kNN 2000 x 100000 x 256 bit, k=2, radius 128, reference tie order", "ms_per_call": ms, "kernel_ms": kms,
+           "pairs_per_s": pairs / (ms * 1e-3), "popc32_equiv_per_s": pairs * 8 / (ms * 1e-3), "planted_neighbours_found": ok,
+           "queries_per_s": 2000 / (ms * 1e-3)}
+    fe.close()
+    log("c4 done: %s" % out)
+    return out
+
+
+def bench_c5(torch, dist, L, fe, dev, n, rank, world, local, args, log):
+    """configs[4]: log replay in epochs, sharded over the ranks: per epoch every rank detects + describes its shard,
+    the ranks all-gather kept segments + descriptors (NCCL inside liblsf.so), every rank appends them -- moved to the map frame
+    with the odometry poses -- to its replica of the map, and the next epoch is matched against that snapshot.  The log is
+    args.c5_frames frames long in total: each rank cycles through its resident 1 000-frame pool (generating 100 000 distinct
+    frames on the host would take minutes and measure numpy, not the path)."""
+    from lane_slam_b200 import odometry
+    from lane_slam_b200.replay import EpochReplay
+    total, E = args.c5_frames, args.c5_epoch
+    per = min(E // world, n)                            # frames per rank and epoch
+    E = per * world
+    n_epochs = max(1, total // E)
+    tt = np.arange(n_epochs * E)
+    poses = odometry.integrate((tt * 0.1e9) % 1e9, 0.30 + 0.05 * np.sin(tt / 50.0), 0.30 + 0.05 * np.cos(tt / 70.0))
+    fe.map_clear()
+    rp = EpochReplay(fe, rank, world, epoch_frames=E, poses=poses, k=K_NN)
+    ext = torch.cuda.ExternalStream(fe.stream(), device=torch.device("cuda", local))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def run(epochs):
+        nseg = 0
+        for e in epochs:
+            lo, hi = rp.shard(e)
+            off = (e * per) % max(1, n - per)
+            b, mi, md = rp.run_epoch(e, dev[off:off + per], lo)
+            nseg += b.n_segments
+        return nseg
+    run(range(0, min(2, n_epochs)))                       # warm-up epochs (part of the log, not of the timed region)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record(ext)
+    nseg = run(range(min(2, n_epochs), n_epochs))
+    msize = rp.finish()
+    e1.record(ext)
+    if world > 1:
+        dist.barrier()
+    e1.synchronize()
+    dt = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t[0])
+    timed_frames = (n_epochs - min(2, n_epochs)) * E
+    out = {"workload": "%d-frame 640x480 log replay in epochs of %d frames over %d GPU(s): detect + describe per shard, all-gather of kept "
+                       "segments + descriptors, map append with odometry poses, kNN (k=2) of epoch e against the map after epoch e-1"
+                       % (n_epochs * E, E, world),
+           "frames": n_epochs * E, "timed_frames": timed_frames, "epoch_frames": E, "frames_per_s": timed_frames / dt if dt > 0 else None,
+           "seconds": dt, "map_lines_at_end": int(msize), "segments_matched_this_rank": int(nseg),
+           "note": "every rank cycles through its resident 1000-frame pool; brute-force matching against the growing map dominates"}
+    log("c5 done: %s" % out)
+    return out
 
 
 _OUT = None
@@ -399,6 +602,11 @@ def main():
     ap.add_argument("--frames", type=int, default=N_FRAMES, help="frames per step per GPU (default: the 1000-frame workload)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--verbose", action="store_true", help="progress on stderr")
+    ap.add_argument("--parity-frames", type=int, default=64, help="frames of the timed step re-checked by the CPU oracle (0 = skip)")
+    ap.add_argument("--extras", default="c3,c4,c5", help="other BASELINE configs measured after the headline (c3, c4: 1 GPU only)")
+    ap.add_argument("--c3-batch", type=int, default=256)
+    ap.add_argument("--c5-frames", type=int, default=100000, help="length of the replayed log (total over all GPUs)")
+    ap.add_argument("--c5-epoch", type=int, default=1024, help="frames per epoch (total over all GPUs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

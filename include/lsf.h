@@ -203,17 +203,60 @@ LSF_API int lsf_project_filter_batch(lsf_ctx *ctx, const float *pixels_normalize
 LSF_API int lsf_knn_hamming(lsf_ctx *ctx, const uint8_t *query, int nq, const uint8_t *train, int nm, int k,
                             int max_dist, int mem_kind, int32_t *idx, int32_t *dist);
 
-/* Map of accumulated line descriptors (BinaryDescriptorMatcher::add/train/clear,
- * binary_descriptor_matcher.cpp:55-105).  The map is device resident. */
+/* Map of accumulated lines, device resident: per line the segment in the MAP frame, colour, the global id of the frame it
+ * was seen in, and its descriptor.  It is what LSF_STAGE_MATCH / lsf_match_batch search (BinaryDescriptorMatcher::add /
+ * train / clear, binary_descriptor_matcher.cpp:55-105) and what show_map accumulates (src/show_map/src/show_map.py:28-43:
+ * an append-only store of every received segment; RViz places them with the map->duck transform the odometry node
+ * broadcasts, src/odometry/src/odometry.py:110-120). */
 LSF_API int lsf_map_clear(lsf_ctx *ctx);
+/* descriptors only (segment = 0, colour = 255, frame = -1) */
 LSF_API int lsf_map_add(lsf_ctx *ctx, const uint8_t *desc, int n, int mem_kind);
 LSF_API int lsf_map_size(lsf_ctx *ctx);
+/* Append the segments line_sanity kept in the last batch: the ground segment of frame f (robot frame "duck") is moved to the
+ * map frame with that frame's pose, p_map = R(theta_f) p + (x_f, y_f); poses = [n_frames][3] = x, y, theta per frame of the
+ * batch (what lsf_odometry_step integrates), NULL = identity.  frame_base = global id of the batch's first frame. */
+LSF_API int lsf_map_append(lsf_ctx *ctx, const double *poses, int frame_base);
+/* Same for n 72-byte exchange records (layout below; host or device) -- e.g. the gathered records of all ranks.  The pose
+ * of record r is poses[frame_id(r) - pose_frame_base]; records of frames outside [pose_frame_base, +n_poses) are appended
+ * untransformed. */
+LSF_API int lsf_map_append_records(lsf_ctx *ctx, const void *records, int n, int mem_kind, const double *poses, int pose_frame_base,
+                                   int n_poses);
+/* Read lines [first, first + count) back to host arrays (NULL = skip): ground f64 [count][4], colour u8, frame i32, desc u8 [count][32]. */
+LSF_API int lsf_map_read(lsf_ctx *ctx, int first, int count, double *ground, uint8_t *color, int32_t *frame, uint8_t *desc);
+
+/* BinaryDescriptorMatcher::knnMatch (dataset form, binary_descriptor_matcher.cpp:339-424) of every descriptor of the LAST batch
+ * against the map as it is now: match_idx / match_dist [n_segments][k], host or device per mem_kind.  The epoch replay
+ *  detects epoch e, appends the gathered lines of epoch e-1, then matches. */
+LSF_API int lsf_match_batch(lsf_ctx *ctx, int k, int mem_kind, int32_t *match_idx, int32_t *match_dist);
+
+/* Diff-drive odometry of the reference (OdometryNode.getPose / drive, src/odometry/src/odometry.py:66-120): host arithmetic.
+ * stamp_nsecs is the `nsecs` field of the wheels-command stamp (the reference uses only that field).  lsf_odometry_step
+ * returns 1 when the pose was advanced (0 < dt < 0.3), 0 when the reference would skip the update, < 0 on error. */
+typedef struct lsf_odometry { double x, y, theta, last_t, dt; } lsf_odometry;
+LSF_API int lsf_odometry_init(lsf_odometry *st, double stamp_nsecs);
+LSF_API int lsf_odometry_step(lsf_odometry *st, double stamp_nsecs, double vel_left, double vel_right);
 
 /* Multi-GPU exchange step: pack the segments of the last batch that line_sanity kept into 72-byte
  * records  { int32 frame_id (+ frame_base), uint8 color, pad[3], double ground[4], uint8 desc[32] }  in a
  * ctx-owned DEVICE buffer, ready to be all-gathered (NCCL) and appended to every rank's map.  *records stays
  * valid until the next call on the ctx.  Needs LSF_STAGE_GROUND (and LSF_STAGE_DESCRIBE for the descriptors). */
 LSF_API int lsf_pack_kept_records(lsf_ctx *ctx, int frame_base, void **records, int *n_records);
+
+/* The exchange step itself, in the library (no host round trip between packing and the collective):
+ *   lsf_nccl_unique_id   rank 0 creates the 128-byte NCCL id and hands it to the other ranks (any transport);
+ *   lsf_exchange_init    one communicator + double-buffered fixed-capacity slots per ctx; max_records = kept segments one rank
+ *                        may contribute per exchange (0 = 64 per frame of max_batch); world = 1 needs no NCCL;
+ *   lsf_allgather_segments  START the exchange of the last batch's kept segments (needs LSF_STAGE_GROUND): the packing kernel
+ *                        runs on the ctx stream, then ONE ncclAllGather of { count, records } slots and a compaction kernel run on
+ *                        the ctx's exchange stream behind an event, overlapping whatever is launched next (up to two in flight).
+ *                        comm: an ncclComm_t of the caller, or NULL for the ctx's own;
+ *   lsf_exchange_wait    finish the oldest exchange in flight: *records = device array of all ranks' 72-byte records in rank
+ *                        order (= global frame order for contiguous shards), *n_total, counts[rank].
+ * NCCL (libnccl.so.2, e.g. the one PyTorch ships; LSF_NCCL_LIB overrides the name) is loaded at run time; failures -> LSF_E_NCCL. */
+LSF_API int lsf_nccl_unique_id(void *id128);
+LSF_API int lsf_exchange_init(lsf_ctx *ctx, const void *unique_id128, int rank, int world, int max_records);
+LSF_API int lsf_allgather_segments(lsf_ctx *ctx, void *comm, int frame_base);
+LSF_API int lsf_exchange_wait(lsf_ctx *ctx, void **records, int *n_total, int *counts, int counts_cap);
 
 /* First consumer of the path.  Replaces the vote loop of LaneFilterHistogram.generate_measurement_likelihood
  * (src/lane_filter/include/lane_filter/lane_filter.py:82-102, generateVote :123-155) for every frame of the last batch:

@@ -40,7 +40,13 @@ class LsfSegments(C.Structure):
     ]
 
 
+class LsfOdometry(C.Structure):
+    _fields_ = [("x", C.c_double), ("y", C.c_double), ("theta", C.c_double), ("last_t", C.c_double), ("dt", C.c_double)]
+
+
 _EXPORTS = [
+    "lsf_map_append", "lsf_map_append_records", "lsf_map_read", "lsf_match_batch", "lsf_odometry_init", "lsf_odometry_step",
+    "lsf_nccl_unique_id", "lsf_exchange_init", "lsf_allgather_segments", "lsf_exchange_wait",
     "lsf_default_config", "lsf_create", "lsf_destroy", "lsf_last_error", "lsf_set_color_transform", "lsf_set_chunk_frames",
     "lsf_set_tie_order", "lsf_capacities", "lsf_cancel_prefetch",
     "lsf_front_end_batch", "lsf_prefetch_batch", "lsf_detect_batch", "lsf_describe_batch", "lsf_project_filter_batch",
@@ -89,6 +95,16 @@ def load():
     lib.lsf_map_clear.argtypes = [vp]
     lib.lsf_map_add.argtypes = [vp, vp, i32, i32]
     lib.lsf_map_size.argtypes = [vp]
+    lib.lsf_map_append.argtypes = [vp, vp, i32]
+    lib.lsf_map_append_records.argtypes = [vp, vp, i32, i32, vp, i32, i32]
+    lib.lsf_map_read.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+    lib.lsf_match_batch.argtypes = [vp, i32, i32, vp, vp]
+    lib.lsf_odometry_init.argtypes = [C.POINTER(LsfOdometry), C.c_double]
+    lib.lsf_odometry_step.argtypes = [C.POINTER(LsfOdometry), C.c_double, C.c_double, C.c_double]
+    lib.lsf_nccl_unique_id.argtypes = [vp]
+    lib.lsf_exchange_init.argtypes = [vp, vp, i32, i32, i32]
+    lib.lsf_allgather_segments.argtypes = [vp, vp, i32]
+    lib.lsf_exchange_wait.argtypes = [vp, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), i32]
     lib.lsf_reset_sequence.argtypes = [vp]
     lib.lsf_get_tap.argtypes = [vp, i32, i32, vp, sz]
     lib.lsf_image_dims.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]

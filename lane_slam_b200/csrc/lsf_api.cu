@@ -1,14 +1,5 @@
 // lsf_api.cu -- the C ABI (include/lsf.h): context, device scratch, batch pipeline, copies.
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <cmath>
-#include <string>
-#include <vector>
-
-#include "common.cuh"
-
-#include <mutex>
+#include "ctx.cuh"
 
 namespace lsf {
 static thread_local long long t_launch_sink = 0;
@@ -16,91 +7,7 @@ thread_local long long *t_launches = &t_launch_sink;
 }
 using namespace lsf;
 
-static std::string g_create_error;
-
-struct StageTime { const char *name; cudaEvent_t ev; };
-
-struct lsf_ctx {
-    lsf_config cfg;
-    int device;
-    cudaStream_t st;
-    Buffers b;
-    Dims d;            // geometry of the last batch
-    ColorParams cp;
-    CamParams cam;
-    int max_batch, max_src_h, max_src_w;
-    int h, w, wp, sh, sw, swp, pixcap, segcap;
-    bool have_batch;
-    const u8 *last_src;   // device pointer of the last batch's frames
-    // map of descriptors
-    u8 *map;              // [map_cap][32] descriptors of the accumulated map lines (what LSF_STAGE_MATCH reads)
-    double *map_ground;   // [map_cap][4] segments in the map frame
-    u8 *map_color;        // [map_cap]
-    int *map_frame;       // [map_cap] global frame id the line was seen in (-1: added through lsf_map_add)
-    int map_n, map_cap;
-    double *pose_dev; int pose_cap;   // {x, y, cos, sin} per frame, staging of lsf_map_append_records
-    // exchange step (lsf_exchange_init / lsf_allgather_segments / lsf_exchange_wait)
-    struct Exchange {
-        void *comm; bool own_comm; int rank, world, cap;      // cap: records per rank and exchange
-        size_t slot_bytes;
-        u8 *send[2], *recv[2], *gathered[2]; int *meta[2];    // double buffered: the gather of step i overlaps step i+1
-        int *h_meta;                                          // pinned [2][world + 2]
-        cudaStream_t st; cudaEvent_t ev_packed[2], ev_done[2];
-        int parity; bool pending[2];
-    } ex;
-    void *knn_scratch;
-    size_t knn_scratch_cap;
-    u8 *carry;            // descriptors of the last frame of the previous batch
-    int carry_n, carry_cap;
-    // pinned host staging
-    int *h_small;         // [n*3 + n+1 + 4]
-    u8 *tap_tmp;
-    size_t tap_cap;
-    u8 *seg_in;           // staging for describe/project inputs given in host memory
-    size_t seg_in_cap;
-    // TMA
-    TmaDesc tma;
-    const u8 *tma_src; int tma_n, tma_h, tma_w; size_t tma_pitch;
-    u8 *kept_rec;         // packed exchange records of the last batch (lsf_pack_kept_records)
-    int last_S, last_stages;
-    // staged input: two staging buffers; a prefetch (lsf_prefetch_batch) fills one while the other is being processed
-    struct Staged { const u8 *host; int n, h, w; size_t pitch; cudaEvent_t ev; bool valid; unsigned long long seq; };
-    u8 *stage_buf[2];
-    Staged staged[2];
-    unsigned long long stage_seq;
-    // chunk pipeline: copy stream, compute streams, per-chunk events
-    cudaStream_t copy_st;
-    cudaStream_t aux[8];
-    std::vector<cudaEvent_t> ev_copy, ev_done, ev_off, ev_lbd;
-    cudaEvent_t ev_begin;
-    // timing
-    std::vector<StageTime> events;
-    int n_events;
-    long long launches;          // kernels launched on behalf of this ctx
-    std::mutex ai_mu;            // guards cfg.ai_scale / ai_shift (lsf_set_color_transform may run concurrently with a batch)
-    bool last_src_valid;         // LSF_TAP_IMAGE: the frames of the last batch are still where last_src points
-    std::string err;
-};
-
-#define CK(call)                                                                                       \
-    do {                                                                                               \
-        cudaError_t e_ = (call);                                                                       \
-        if (e_ != cudaSuccess) {                                                                       \
-            char buf_[512];                                                                            \
-            snprintf(buf_, sizeof(buf_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-            ctx->err = buf_;                                                                           \
-            return LSF_E_CUDA;                                                                         \
-        }                                                                                              \
-    } while (0)
-
-// entry of every call that touches the device: select the ctx's device, count launches on the ctx
-#define ENTER(ctx) do { CK(cudaSetDevice((ctx)->device)); lsf::t_launches = &(ctx)->launches; } while (0)
-
-static int fail(lsf_ctx *ctx, int code, const std::string &msg)
-{
-    if (ctx) ctx->err = msg; else g_create_error = msg;
-    return code;
-}
+std::string g_create_error;
 
 // ---- defaults (the reference's YAML files) --------------------------------------------------------------
 extern "C" int lsf_default_config(lsf_config *c)
@@ -128,11 +35,6 @@ extern "C" int lsf_default_config(lsf_config *c)
     return LSF_OK;
 }
 
-template <typename T>
-static cudaError_t dalloc(T **p, size_t count)
-{
-    return cudaMalloc((void **)p, (count ? count : 1) * sizeof(T));
-}
 
 extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
 {
@@ -274,7 +176,7 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
 #undef CKC
 }
 
-static void exchange_destroy(lsf_ctx *ctx);
+void exchange_destroy(lsf_ctx *ctx);
 
 extern "C" void lsf_destroy(lsf_ctx *ctx)
 {
@@ -385,7 +287,7 @@ static void make_tma(lsf_ctx *ctx, const u8 *src, int n, int sh, int sw, size_t 
     ctx->tma_src = src; ctx->tma_n = n; ctx->tma_h = sh; ctx->tma_w = sw; ctx->tma_pitch = pitch;
 }
 
-static void mark(lsf_ctx *ctx, const char *name)
+void mark(lsf_ctx *ctx, const char *name)
 {
     if (g_debug_sync) {
         cudaError_t e = cudaStreamSynchronize(ctx->st);
@@ -454,9 +356,9 @@ extern "C" int lsf_cancel_prefetch(lsf_ctx *ctx)
     return LSF_OK;
 }
 
-static cudaMemcpyKind out_kind(int mem) { return mem == LSF_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost; }
+cudaMemcpyKind out_kind(int mem) { return mem == LSF_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost; }
 
-static int ensure_knn(lsf_ctx *ctx, int nq, int nm, int k)
+int ensure_knn(lsf_ctx *ctx, int nq, int nm, int k)
 {
     size_t need = knn_scratch_bytes(nq, nm, k);
     if (need > ctx->knn_scratch_cap) {
@@ -711,7 +613,7 @@ extern "C" int lsf_detect_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int src
     return lsf_front_end_batch(ctx, bgr, n, src_h, src_w, pitch, mem_kind, LSF_STAGE_DETECT, 0, out);
 }
 
-static int stage_in(lsf_ctx *ctx, size_t bytes)
+int stage_in(lsf_ctx *ctx, size_t bytes)
 {
     if (bytes > ctx->seg_in_cap) {
         if (ctx->seg_in) cudaFree(ctx->seg_in);
@@ -876,137 +778,6 @@ extern "C" int lsf_reset_sequence(lsf_ctx *ctx)
 {
     if (!ctx) return LSF_E_ARG;
     ctx->carry_n = 0;
-    return LSF_OK;
-}
-
-// grow the map arrays (descriptors, segments, colour, frame id) to hold `need` lines
-static int map_reserve(lsf_ctx *ctx, int need)
-{
-    if (need <= ctx->map_cap) return LSF_OK;
-    int ncap = std::max(std::max(ctx->map_cap * 2, need), 4096);
-    u8 *nd = nullptr, *nc = nullptr; double *ng = nullptr; int *nf = nullptr;
-    CK(cudaMalloc((void **)&nd, (size_t)ncap * 32)); CK(cudaMalloc((void **)&ng, (size_t)ncap * 32));
-    CK(cudaMalloc((void **)&nc, (size_t)ncap)); CK(cudaMalloc((void **)&nf, (size_t)ncap * 4));
-    if (ctx->map_n) {
-        CK(cudaMemcpyAsync(nd, ctx->map, (size_t)ctx->map_n * 32, cudaMemcpyDeviceToDevice, ctx->st));
-        CK(cudaMemcpyAsync(ng, ctx->map_ground, (size_t)ctx->map_n * 32, cudaMemcpyDeviceToDevice, ctx->st));
-        CK(cudaMemcpyAsync(nc, ctx->map_color, (size_t)ctx->map_n, cudaMemcpyDeviceToDevice, ctx->st));
-        CK(cudaMemcpyAsync(nf, ctx->map_frame, (size_t)ctx->map_n * 4, cudaMemcpyDeviceToDevice, ctx->st));
-    }
-    CK(cudaStreamSynchronize(ctx->st));
-    for (void *p : {(void *)ctx->map, (void *)ctx->map_ground, (void *)ctx->map_color, (void *)ctx->map_frame}) if (p) cudaFree(p);
-    ctx->map = nd; ctx->map_ground = ng; ctx->map_color = nc; ctx->map_frame = nf; ctx->map_cap = ncap;
-    return LSF_OK;
-}
-
-extern "C" int lsf_map_add(lsf_ctx *ctx, const uint8_t *desc, int n, int mem_kind)
-{
-    if (!ctx || n < 0 || (n > 0 && !desc)) return LSF_E_ARG;
-    if (n == 0) return LSF_OK;
-    ENTER(ctx);
-    int rc = map_reserve(ctx, ctx->map_n + n);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(ctx->map + (size_t)ctx->map_n * 32, desc, (size_t)n * 32,
-                       mem_kind == LSF_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemsetAsync(ctx->map_ground + (size_t)ctx->map_n * 4, 0, (size_t)n * 32, ctx->st));
-    CK(cudaMemsetAsync(ctx->map_color + ctx->map_n, 0xff, (size_t)n, ctx->st));
-    CK(cudaMemsetAsync(ctx->map_frame + ctx->map_n, 0xff, (size_t)n * 4, ctx->st));
-    CK(cudaStreamSynchronize(ctx->st));
-    ctx->map_n += n;
-    return LSF_OK;
-}
-
-extern "C" int lsf_map_append_records(lsf_ctx *ctx, const void *records, int n, int mem_kind, const double *poses, int pose_frame_base,
-                                      int n_poses)
-{
-    if (!ctx || n < 0 || (n > 0 && !records) || n_poses < 0 || (n_poses > 0 && !poses)) return LSF_E_ARG;
-    if (n == 0) return LSF_OK;
-    ENTER(ctx);
-    int rc = map_reserve(ctx, ctx->map_n + n);
-    if (rc) return rc;
-    const u8 *rec = (const u8 *)records;
-    if (mem_kind != LSF_MEM_DEVICE) {
-        rc = stage_in(ctx, (size_t)n * 72);
-        if (rc) return rc;
-        CK(cudaMemcpyAsync(ctx->seg_in, records, (size_t)n * 72, cudaMemcpyHostToDevice, ctx->st));
-        rec = ctx->seg_in;
-    }
-    if (n_poses > 0) {
-        // {x, y, cos(theta), sin(theta)}: the trigonometry is done here, with the host libm the reference itself runs on
-        std::vector<double> p4((size_t)n_poses * 4);
-        for (int i = 0; i < n_poses; ++i) {
-            p4[4 * i] = poses[3 * i]; p4[4 * i + 1] = poses[3 * i + 1];
-            p4[4 * i + 2] = cos(poses[3 * i + 2]); p4[4 * i + 3] = sin(poses[3 * i + 2]);
-        }
-        if (n_poses > ctx->pose_cap) {
-            if (ctx->pose_dev) cudaFree(ctx->pose_dev);
-            ctx->pose_dev = nullptr; ctx->pose_cap = 0;
-            CK(cudaMalloc((void **)&ctx->pose_dev, (size_t)n_poses * 32));
-            ctx->pose_cap = n_poses;
-        }
-        CK(cudaMemcpyAsync(ctx->pose_dev, p4.data(), (size_t)n_poses * 32, cudaMemcpyHostToDevice, ctx->st));
-        CK(cudaStreamSynchronize(ctx->st));       // p4 goes out of scope
-    }
-    launch_map_append(rec, n, n_poses > 0 ? ctx->pose_dev : nullptr, pose_frame_base, n_poses, ctx->map_n, ctx->map_ground, ctx->map_color,
-                      ctx->map_frame, ctx->map, ctx->st);
-    CK(cudaStreamSynchronize(ctx->st));
-    CK(cudaGetLastError());
-    ctx->map_n += n;
-    return LSF_OK;
-}
-
-extern "C" int lsf_map_append(lsf_ctx *ctx, const double *poses, int frame_base)
-{
-    if (!ctx) return LSF_E_ARG;
-    void *rec = nullptr; int n = 0;
-    int rc = lsf_pack_kept_records(ctx, frame_base, &rec, &n);
-    if (rc) return rc;
-    return lsf_map_append_records(ctx, rec, n, LSF_MEM_DEVICE, poses, frame_base, poses ? ctx->d.n : 0);
-}
-
-extern "C" int lsf_map_read(lsf_ctx *ctx, int first, int count, double *ground, uint8_t *color, int32_t *frame, uint8_t *desc)
-{
-    if (!ctx || first < 0 || count < 0 || first + count > ctx->map_n) return LSF_E_ARG;
-    if (count == 0) return LSF_OK;
-    ENTER(ctx);
-    if (ground) CK(cudaMemcpyAsync(ground, ctx->map_ground + (size_t)first * 4, (size_t)count * 32, cudaMemcpyDeviceToHost, ctx->st));
-    if (color) CK(cudaMemcpyAsync(color, ctx->map_color + first, (size_t)count, cudaMemcpyDeviceToHost, ctx->st));
-    if (frame) CK(cudaMemcpyAsync(frame, ctx->map_frame + first, (size_t)count * 4, cudaMemcpyDeviceToHost, ctx->st));
-    if (desc) CK(cudaMemcpyAsync(desc, ctx->map + (size_t)first * 32, (size_t)count * 32, cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaStreamSynchronize(ctx->st));
-    return LSF_OK;
-}
-
-// k-NN of the descriptors of the last batch against the map, after the fact (the epoch replay appends the previous
-// epoch's gathered lines while this batch is being detected, then matches)
-extern "C" int lsf_match_batch(lsf_ctx *ctx, int k, int mem_kind, int32_t *match_idx, int32_t *match_dist)
-{
-    if (!ctx || !match_idx || !match_dist) return LSF_E_ARG;
-    if (k < 1 || k > 8) return fail(ctx, LSF_E_ARG, "lsf_match_batch: k must be 1..8");
-    if (!ctx->have_batch || !(ctx->last_stages & LSF_STAGE_DESCRIBE))
-        return fail(ctx, LSF_E_ARG, "lsf_match_batch: the last batch must have run LSF_STAGE_DESCRIBE");
-    const int S = ctx->last_S;
-    if (S == 0) return LSF_OK;
-    ENTER(ctx);
-    Buffers &b = ctx->b;
-    if (!b.o_midx) { CK(dalloc(&b.o_midx, (size_t)b.outcap * 8)); CK(dalloc(&b.o_mdist, (size_t)b.outcap * 8)); }
-    if (ctx->map_n <= 0) {
-        CK(cudaMemsetAsync(b.o_midx, 0xff, (size_t)S * k * 4, ctx->st));
-        CK(cudaMemsetAsync(b.o_mdist, 0xff, (size_t)S * k * 4, ctx->st));
-    } else {
-        int rc = ensure_knn(ctx, S, ctx->map_n, k);
-        if (rc) return rc;
-        ctx->n_events = 0;
-        mark(ctx, "start");
-        launch_knn(b.o_desc, S, nullptr, ctx->map, ctx->map_n, k, LSF_MATCH_RADIUS, ctx->cfg.tie_order, b.o_midx, b.o_mdist, ctx->knn_scratch,
-                   ctx->knn_scratch_cap, ctx->st);
-        mark(ctx, "knn");
-    }
-    const cudaMemcpyKind kind = out_kind(mem_kind);
-    CK(cudaMemcpyAsync(match_idx, b.o_midx, (size_t)S * k * 4, kind, ctx->st));
-    CK(cudaMemcpyAsync(match_dist, b.o_mdist, (size_t)S * k * 4, kind, ctx->st));
-    CK(cudaStreamSynchronize(ctx->st));
-    CK(cudaGetLastError());
     return LSF_OK;
 }
 

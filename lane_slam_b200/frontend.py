@@ -294,6 +294,70 @@ class FrontEnd:
         """Append n 32-byte descriptors that already live on the device."""
         self._check(self._lib.lsf_map_add(self._ctx, ptr, int(n), MEM_DEVICE))
 
+    # -- map of accumulated lines / epoch exchange ------------------------------------------------------------
+    def map_append(self, poses=None, frame_base=0):
+        """Append the kept ground segments of the last batch to the device map, moved to the map frame with the per-frame
+        poses [n_frames, 3] = (x, y, theta) (show_map.py:28-43 + the map->duck TF of odometry.py:110-120)."""
+        p = None if poses is None else np.ascontiguousarray(poses, np.float64).reshape(self._last_n, 3)
+        self._check(self._lib.lsf_map_append(self._ctx, None if p is None else p.ctypes.data, int(frame_base)))
+
+    def map_append_records(self, records, n=None, poses=None, pose_frame_base=0):
+        """Append 72-byte exchange records: a numpy structured / uint8 array (host) or a raw device pointer with n."""
+        p = None if poses is None else np.ascontiguousarray(poses, np.float64).reshape(-1, 3)
+        if isinstance(records, np.ndarray):
+            r = np.ascontiguousarray(records).view(np.uint8).reshape(-1, 72)
+            ptr, n, kind = r.ctypes.data, len(r), MEM_HOST
+        else:
+            ptr, kind = int(records), MEM_DEVICE
+        self._check(self._lib.lsf_map_append_records(self._ctx, ptr, int(n), kind, None if p is None else p.ctypes.data,
+                                                     int(pose_frame_base), 0 if p is None else len(p)))
+
+    def map_read(self, first=0, count=None):
+        """-> dict(ground f64 [M,4] in the map frame, color u8 [M], frame i32 [M], desc u8 [M,32])."""
+        count = self.map_size() - first if count is None else count
+        g = np.empty((count, 4), np.float64); c = np.empty(count, np.uint8); f = np.empty(count, np.int32)
+        d = np.empty((count, 32), np.uint8)
+        self._check(self._lib.lsf_map_read(self._ctx, int(first), int(count), g.ctypes.data, c.ctypes.data, f.ctypes.data, d.ctypes.data))
+        return dict(ground=g, color=c, frame=f, desc=d)
+
+    def match_batch(self, n_segments, k=2):
+        """kNN of the last batch's descriptors against the map as it is now -> (idx, dist) i32 [S, k]."""
+        idx = np.empty((n_segments, k), np.int32); dist = np.empty((n_segments, k), np.int32)
+        self._check(self._lib.lsf_match_batch(self._ctx, int(k), MEM_HOST, idx.ctypes.data, dist.ctypes.data))
+        return idx, dist
+
+    def exchange_init(self, rank=0, world=1, unique_id=None, max_records=0):
+        """One NCCL communicator per ctx for the epoch exchange (world = 1 needs none).  unique_id: the 128 bytes rank 0 got
+        from nccl_unique_id(), handed to every rank by any transport (torch.distributed broadcast in bench.py)."""
+        uid = None if unique_id is None else (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self._lib.lsf_exchange_init(self._ctx, uid, int(rank), int(world), int(max_records)))
+        self._world = int(world)
+
+    def allgather_start(self, frame_base=0):
+        """Start the exchange of the last batch's kept segments (returns at once; overlaps the next batch)."""
+        self._check(self._lib.lsf_allgather_segments(self._ctx, None, int(frame_base)))
+
+    def exchange_wait(self):
+        """Finish the oldest exchange -> (device pointer of the gathered 72-byte records, total, per-rank counts)."""
+        ptr, n = C.c_void_p(), C.c_int()
+        counts = (C.c_int * self._world)()
+        self._check(self._lib.lsf_exchange_wait(self._ctx, C.byref(ptr), C.byref(n), counts, self._world))
+        return ptr.value, n.value, list(counts)
+
+    def read_device_records(self, ptr, n):
+        """Copy n 72-byte records from a device pointer to a host structured array (dist._REC layout)."""
+        from . import dist as _dist
+        out = np.zeros(n, _dist._REC)
+        if n:
+            import ctypes
+            cudart = ctypes.CDLL("libcudart.so.12") if not hasattr(self, "_cudart") else self._cudart
+            self._cudart = cudart
+            cudart.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+            rc = cudart.cudaMemcpy(out.ctypes.data, ptr, n * 72, 2)
+            if rc != 0:
+                raise LsfError(_lib.LSF_E_CUDA, "cudaMemcpy of exchange records failed: %d" % rc)
+        return out
+
     def lane_votes(self, delta_d=0.02, delta_phi=0.1):
         """Vote histograms of the last batch, int32 [n_frames, nd, nphi]: the counts that
         LaneFilterHistogram.generate_measurement_likelihood (lane_filter.py:82-102) accumulates before normalising.

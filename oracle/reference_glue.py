@@ -327,3 +327,25 @@ def knn_hamming_bf(q, m, k):
             idx[i, j] = dm.trainIdx
             dist[i, j] = int(dm.distance)
     return idx, dist
+
+
+def map_transform(ground, frame_ids, poses, pose_frame_base=0):
+    """What RViz does with show_map's markers (frame '/duck', src/show_map/src/show_map.py:45-75) and the map->duck transform
+    the odometry node broadcasts (src/odometry/src/odometry.py:110-120: translation (x, y, 0), rotation theta about z):
+    p_map = R(theta) p_duck + (x, y), per segment with the pose of ITS frame.  ground f64 [S,4] -> f64 [S,4]."""
+    ground = np.asarray(ground, np.float64).reshape(-1, 4)
+    out = ground.copy()
+    if poses is None:
+        return out
+    poses = np.asarray(poses, np.float64).reshape(-1, 3)
+    for i, f in enumerate(np.asarray(frame_ids)):
+        pf = int(f) - pose_frame_base
+        if pf < 0 or pf >= len(poses):
+            continue
+        x, y, th = poses[pf]
+        c, s = np.cos(th), np.sin(th)
+        for o in (0, 2):
+            px, py = ground[i, o], ground[i, o + 1]
+            out[i, o] = (c * px - s * py) + x
+            out[i, o + 1] = (s * px + c * py) + y
+    return out

@@ -571,3 +571,84 @@ def test_host_capacity_grows_and_stale_prefetch_is_dropped(mods):
     assert np.array_equal(got, want1) and not np.array_equal(got, want0)
     fe.prefetch(buf); fe.cancel_prefetch()
     fe.close()
+
+
+def test_map_append_with_odometry_poses(mods):
+    """kept ground segments moved to the map frame with per-frame odometry poses and appended to the device map
+    (segment, colour, frame id, descriptor); the map is what LSF_STAGE_MATCH / lsf_match_batch then search."""
+    from lane_slam_b200 import dist as ldist, odometry
+    L, cm, rg, synth, cfg = mods
+    frames = synth.sequence(6, base_seed=40)
+    g = np.load(__file__.replace("test_gpu_parity.py", "golden/odometry.npz"))
+    poses = odometry.integrate(g["nsecs"][:12], g["vel_left"][:12], g["vel_right"][:12])
+    assert np.array_equal(poses, g["poses"][:12])
+    fe, cam, Hg = _front_end(L, rg, (480, 640), 0, 480, 640, 6)
+    st = L.STAGE_DETECT | L.STAGE_GROUND | L.STAGE_DESCRIBE
+    want = dict(ground=[], color=[], frame=[], desc=[])
+    for part in range(2):
+        fr = frames[3 * part:3 * part + 3]
+        b = fe.process(fr, stages=st)
+        fe.map_append(poses[3 * part + 2:3 * part + 5], frame_base=100 + 3 * part)     # any pose slice: frame f -> poses[f]
+        rec = ldist.unpack(ldist.pack_kept(b, frame_base=100 + 3 * part))
+        want["ground"].append(rg.map_transform(rec["ground"], rec["frame"], poses[3 * part + 2:3 * part + 5], 100 + 3 * part))
+        for k in ("color", "frame", "desc"):
+            want[k].append(rec[k])
+    m = fe.map_read()
+    assert fe.map_size() == sum(len(x) for x in want["color"]) > 0
+    for k in ("color", "frame", "desc"):
+        assert np.array_equal(m[k], np.concatenate(want[k])), k
+    assert np.abs(m["ground"] - np.concatenate(want["ground"])).max() <= GROUND_TOL_M
+    assert np.array_equal(m["ground"], np.concatenate(want["ground"]))            # observed: exact
+    # the map is searchable: every kept line of the last batch finds itself at distance 0
+    idx, dist = fe.match_batch(b.n_segments, k=1)
+    kept = b.keep.astype(bool)
+    assert (dist[kept, 0] == 0).all() and np.array_equal(m["desc"][idx[kept, 0]], b.desc[kept])
+    fe.close()
+
+
+def test_epoch_replay_gpu_equals_host_backend(mods):
+    """BASELINE configs[4] semantics on one GPU (exchange with world = 1: same kernels, no NCCL): the epoch loop over the
+    library (pack -> gather -> compact on the exchange stream, map append with poses, match against the snapshot after
+    epoch e-1) gives the map and the matches of the oracle-backed host loop."""
+    from host_backend import HostBackend
+    from lane_slam_b200.replay import EpochReplay
+    L, cm, rg, synth, cfg = mods
+    n_total, E, H, W = 20, 8, 240, 320
+    cam, Hg = rg.scaled_camera(W, H)
+    rng = np.random.default_rng(3)
+    poses = np.cumsum(rng.normal(0, 0.02, (n_total, 3)), axis=0)
+    fe = L.FrontEnd(dict(L.DEFAULT_DETECTOR_CONFIGURATION), img_size=(H, W), top_cutoff=0, camera=cam, homography=Hg, src_size=(H, W),
+                    max_batch=E, max_segments_per_frame=2048)
+    fe.exchange_init(rank=0, world=1)
+    runs = []
+    for be in (fe, HostBackend(cfg, (H, W), 0, cam, Hg)):
+        rp = EpochReplay(be, 0, 1, epoch_frames=E, poses=poses, k=2)
+        out = []
+        for e in range((n_total + E - 1) // E):
+            lo, hi = rp.shard(e, n_total)
+            b, mi, md = rp.run_epoch(e, synth.sequence(hi - lo, base_seed=0, H=H, W=W, start=lo), lo)
+            out.append((mi.copy(), md.copy()))
+        rp.finish()
+        runs.append((be.map_read(), out))
+    (gm, go), (hm, ho) = runs
+    assert len(hm["desc"]) > 0 and fe.map_size() == len(hm["desc"])
+    for k in ("color", "frame", "desc"):
+        assert np.array_equal(gm[k], hm[k]), k
+    assert np.abs(gm["ground"] - hm["ground"]).max() <= GROUND_TOL_M
+    for (gi, gd), (hi_, hd) in zip(go, ho):
+        assert np.array_equal(gi, hi_) and np.array_equal(gd, hd)
+    fe.close()
+
+
+def test_exchange_two_ranks_nccl(mods):
+    """Two ranks, two GPUs, NCCL inside liblsf.so (lsf_allgather_segments): skipped on a one-GPU box; bench.py --gpus 2 and
+    tests/gpu_replay_multirank.py cover it there."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = __file__.replace("test_gpu_parity.py", "gpu_replay_multirank.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29541", script], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "replay multirank ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
