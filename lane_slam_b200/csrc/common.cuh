@@ -135,6 +135,19 @@ void launch_seg_offsets(const Dims &d, Buffers &b, cudaStream_t st);
 void launch_segments(const Dims &d, const CamParams &cam, Buffers &b, int do_ground, cudaStream_t st);
 void launch_lane_votes(const CamParams &cam, int nseg, double delta_d, double delta_phi, int nd, int nphi, const Buffers &b, int *hist,
                        cudaStream_t st);
+// lane filter (k_lane_filter.cu): histogram geometry + numpy's pairwise-summation plan for nd * nphi cells (host-made)
+constexpr int LF_MAX_LEAVES = 32;
+struct LaneFilterPlan {
+    int nd, nphi, r_d, r_phi;
+    double d_min, d_max, phi_min, phi_max, delta_d, delta_phi;
+    int nleaf, ncomb;
+    short leaf_off[LF_MAX_LEAVES], leaf_len[LF_MAX_LEAVES];
+    unsigned char comb_a[LF_MAX_LEAVES], comb_b[LF_MAX_LEAVES];
+};
+size_t lane_filter_smem(int ncell);
+void launch_lane_filter(const LaneFilterPlan &pl, int n_frames, int use_propagation, const double *dt_v_w, const int *hist,
+                        const double *d_grid, const double *phi_grid, const double *sin_phi, const double *w_d, const double *w_phi,
+                        double *belief, double *est, cudaStream_t st);
 void launch_pack_kept(int nseg, int frame_base, const Buffers &b, u8 *rec, int cap, int *count, cudaStream_t st);
 void launch_gather_compact(const u8 *slots, size_t slot_bytes, int world, int cap, u8 *out, int *meta, cudaStream_t st);
 void launch_map_append(const u8 *rec, int n, const double *pose4, int pose_base, int n_pose, int map_n, double *m_ground, u8 *m_color,
