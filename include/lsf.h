@@ -86,7 +86,11 @@ typedef struct lsf_config {
                                     frames already on the device, one chunk below 64 frames), < 0 = never chunk (one
                                     stream; lsf_last_timings then lists every kernel) */
     int32_t tie_order;           /* LSF_TIES_REFERENCE (0, default) or LSF_TIES_INDEX */
-    int32_t reserved[5];
+    int32_t grow_warps_per_sm;   /* persistent region-growing warps per SM (0 = default 16, the fastest for ONE batch in flight).
+                                    Each holds ~122 registers x 32 lanes; with several contexts in flight on one GPU (one
+                                    host thread each) 6-10 leave room for the dense kernels of the other batches, so that
+                                    the latency-bound search of one batch runs under the issue-bound kernels of another */
+    int32_t reserved[4];
 } lsf_config;
 
 /*
@@ -266,6 +270,29 @@ LSF_API int lsf_exchange_wait(lsf_ctx *ctx, void **records, int *n_total, int *c
  * widths are those of lsf_config (identical in the reference's line_sanity and lane_filter defaults).
  * Needs LSF_STAGE_GROUND in the last batch. */
 LSF_API int lsf_lane_votes(lsf_ctx *ctx, double delta_d, double delta_phi, int nd, int nphi, int mem_kind, int32_t *hist);
+
+/* The whole histogram lane filter for the frames of the last batch, in order: per frame predict(dt, v, w) (optional), update with
+ * the frame's votes, getEstimate / getMax -- LaneFilterHistogram.predict / update / getEstimate / getMax
+ * (src/lane_filter/include/lane_filter/lane_filter.py:47-112) as LaneFilterNode.processSegments drives them
+ * (src/lane_filter/src/lane_filter_node.py:53-65).  The belief lives on the device between batches.  Bit-identical to the
+ * reference class: every float64 operation in numpy's / scipy.ndimage's order; the tables that involve transcendental functions
+ * come from the host (numpy / scipy there are what the reference calls):
+ *   d_grid, phi_grid [nd*nphi]  np.mgrid[d_min:d_max:delta_d, phi_min:phi_max:delta_phi]          (lane_filter.py:38)
+ *   sin_phi [nd*nphi]           np.sin(phi_grid)                                                    (:49)
+ *   w_d [r_d + 1], w_phi [r_phi + 1]   scipy.ndimage Gaussian mask weights at distance 0 .. r for sigma_d_mask / sigma_phi_mask,
+ *                               r = int(4 sigma + 0.5)                                              (:66, gaussian_filter)
+ *   belief0 [nd*nphi]           multivariate_normal(mean_0, cov_0).pdf(grid)                        (:114-120)
+ * lsf_lane_filter_batch: dt_v_w [n_frames][3] host (NULL when use_propagation = 0); estimates [n_frames][3] host = d, phi of the
+ * belief's arg-max cell centre and the belief maximum after each frame. */
+typedef struct lsf_lane_filter_config {
+    int32_t nd, nphi, r_d, r_phi;
+    double d_min, d_max, phi_min, phi_max, delta_d, delta_phi;
+    const double *d_grid, *phi_grid, *sin_phi, *w_d, *w_phi, *belief0;
+} lsf_lane_filter_config;
+LSF_API int lsf_lane_filter_init(lsf_ctx *ctx, const lsf_lane_filter_config *cfg);
+LSF_API int lsf_lane_filter_reset(lsf_ctx *ctx);                 /* belief <- belief0 (LaneFilterHistogram.initialize) */
+LSF_API int lsf_lane_filter_batch(lsf_ctx *ctx, const double *dt_v_w, int use_propagation, double *estimates);
+LSF_API int lsf_lane_filter_belief(lsf_ctx *ctx, double *belief); /* [nd*nphi] host */
 
 /* Forget the previous batch's last frame (start of a new sequence for LSF_STAGE_MATCH_PREV). */
 LSF_API int lsf_reset_sequence(lsf_ctx *ctx);

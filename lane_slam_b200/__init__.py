@@ -11,6 +11,7 @@ from ._lib import (LsfError, STAGE_DESCRIBE, STAGE_DETECT, STAGE_GROUND, STAGE_M
 from .frontend import (FrontEnd, SegmentBatch, DEFAULT_DETECTOR_CONFIGURATION, DETECTOR_PARAM_NAMES, COLORS,
                        WHITE, YELLOW, RED, scaled_calibration, check_detector_configuration)
 from .line_detector import LineDetectorB200, Detections, LineDetectorInterface
+from .lane_filter import LaneFilterB200
 from .messages import Segment, SegmentList, Vector2D, Point, segment_lists_from_batch
 
 STAGE_ALL = STAGE_DETECT | STAGE_GROUND | STAGE_DESCRIBE

@@ -26,7 +26,7 @@ class LsfConfig(C.Structure):
         ("d_min", C.c_double), ("d_max", C.c_double), ("phi_min", C.c_double), ("phi_max", C.c_double),
         ("max_batch", C.c_int32), ("max_src_h", C.c_int32), ("max_src_w", C.c_int32),
         ("max_segments_per_color", C.c_int32), ("max_pixels_per_color", C.c_int32), ("device", C.c_int32),
-        ("chunk_frames", C.c_int32), ("tie_order", C.c_int32), ("reserved", C.c_int32 * 5),
+        ("chunk_frames", C.c_int32), ("tie_order", C.c_int32), ("grow_warps_per_sm", C.c_int32), ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -47,6 +47,7 @@ class LsfOdometry(C.Structure):
 _EXPORTS = [
     "lsf_map_append", "lsf_map_append_records", "lsf_map_read", "lsf_match_batch", "lsf_odometry_init", "lsf_odometry_step",
     "lsf_nccl_unique_id", "lsf_exchange_init", "lsf_allgather_segments", "lsf_exchange_wait",
+    "lsf_lane_filter_init", "lsf_lane_filter_reset", "lsf_lane_filter_batch", "lsf_lane_filter_belief",
     "lsf_default_config", "lsf_create", "lsf_destroy", "lsf_last_error", "lsf_set_color_transform", "lsf_set_chunk_frames",
     "lsf_set_tie_order", "lsf_capacities", "lsf_cancel_prefetch",
     "lsf_front_end_batch", "lsf_prefetch_batch", "lsf_detect_batch", "lsf_describe_batch", "lsf_project_filter_batch",
@@ -101,6 +102,10 @@ def load():
     lib.lsf_match_batch.argtypes = [vp, i32, i32, vp, vp]
     lib.lsf_odometry_init.argtypes = [C.POINTER(LsfOdometry), C.c_double]
     lib.lsf_odometry_step.argtypes = [C.POINTER(LsfOdometry), C.c_double, C.c_double, C.c_double]
+    lib.lsf_lane_filter_init.argtypes = [vp, vp]
+    lib.lsf_lane_filter_reset.argtypes = [vp]
+    lib.lsf_lane_filter_batch.argtypes = [vp, vp, i32, vp]
+    lib.lsf_lane_filter_belief.argtypes = [vp, vp]
     lib.lsf_nccl_unique_id.argtypes = [vp]
     lib.lsf_exchange_init.argtypes = [vp, vp, i32, i32, i32]
     lib.lsf_allgather_segments.argtypes = [vp, vp, i32]

@@ -40,6 +40,9 @@ struct Dims {
     int min_reg;           // LSD: int(-logNT / log10(22.5 / 180)), smallest region worth a rectangle
     int grow_per_sm;       // persistent growing warps per SM for this launch (fewer when chunks overlap: leaves registers
                            // and issue slots to the dense kernels of the other chunk)
+    int grow_used_bits;    // size of the shared-memory USED bitmap of a growing warp, in support pixels (0 = pixcap): the largest
+                           // per-image support-pixel count of the previous batch plus head-room; an image that exceeds it is
+                           // reported through flags[5] and the batch is redone with the full size
     int f0;                // first frame of this launch inside the batch (TMA coordinate, frame ids of the output rows;
                            // every per-frame / per-image buffer is pre-offset to the chunk)
 };
@@ -55,6 +58,7 @@ struct __align__(16) LsdPix {
     u32 g2;         // gx^2 + gy^2 (norm = sqrt(g2/4))
 };
 constexpr u32 LSD_NONE = 0xffffffffu;
+constexpr int LSD_FAT_WORDS = 32;   // words per neighbour record of a support pixel (k_lsd_core.cu)
 constexpr int LSD_MAXC = 1024;   // growing tasks per colour image (component slot s -> task s % LSD_MAXC)
 
 // parameters handed to kernels by value
@@ -91,7 +95,7 @@ struct Buffers {
     LsdPix *pix;        // [n*3][pixcap]
     u32 *pxy;           // [n*3][pixcap]  (y << 16) | x in the scaled image
     float2 *scs;        // [n*3][pixcap]  float(cos), float(sin) of the double angle (sums of a region seeded here)
-    u32 *fat;           // [n*3][pixcap][40] per pixel: index, angle, cos, sin, g2 of its 8 neighbours (LSD_NONE = undefined)
+    u32 *fat;           // [n*3][pixcap][LSD_FAT_WORDS] per pixel: index, angle, cos, sin of its 8 neighbours (LSD_NONE = undefined)
     u32 *order;         // [n*3][pixcap]  seed order (compact indices)
     u32 *label, *csize, *coff;   // [n*3][pixcap] connected components: root label, size (at roots), seed-list cursor (at roots)
     u32 *corder, *cpos; // [n*3][pixcap]  seed order partitioned by component; position of each entry in order[]
@@ -113,7 +117,8 @@ struct Buffers {
     int *segcount;      // [n*3]
     int *frame_off;     // [n+1]          first output row of every frame (global: chunks chain through it)
     int *imgoff;        // [n*3]          first output row of every colour image
-    int *flags;         // [4] 0 pix overflow, 1 seg/candidate overflow, 2 out capacity, 3 candidate counter
+    int *flags;         // [8] 0 pix overflow, 1 seg/candidate overflow, 2 out capacity, 3 LBD cursor (lsf_describe_batch), 4 pack counter,
+                        //     5 support pixels of an image that did not fit the USED bitmap of the growing kernel
     // compacted per-segment outputs (capacity outcap)
     int outcap;
     u8 *o_color; float *o_lines; double *o_normals; float *o_centers; float *o_pixn; float *o_nf32;
@@ -129,7 +134,7 @@ void launch_color_canny(const Dims &d, const ColorParams &cp, const u8 *src, con
                         u8 *gray, cudaStream_t st);
 void launch_hysteresis(const Dims &d, int dilate, const u32 *planesA, u32 *planesB, cudaStream_t st);
 void launch_lsd_pre(const Dims &d, const u32 *planesB, Buffers &b, cudaStream_t st);
-void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st);      // seeds + region growing + refine
+void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st, cudaEvent_t ev_indexed = nullptr);      // seeds + region growing + refine
 void launch_lsd_validate(const Dims &d, Buffers &b, cudaStream_t st);  // NFA validation + emit
 void launch_seg_offsets(const Dims &d, Buffers &b, cudaStream_t st);
 void launch_segments(const Dims &d, const CamParams &cam, Buffers &b, int do_ground, cudaStream_t st);

@@ -33,6 +33,7 @@ struct lsf_ctx {
     u8 *map_color;        // [map_cap]
     int *map_frame;       // [map_cap] global frame id the line was seen in (-1: added through lsf_map_add)
     int map_n, map_cap;
+    void *lane_filter;    // LaneFilterState (lsf_map_exchange.cu), or NULL
     double *pose_dev; int pose_cap;   // {x, y, cos, sin} per frame, staging of lsf_map_append_records
     // exchange step (lsf_exchange_init / lsf_allgather_segments / lsf_exchange_wait)
     struct Exchange {
@@ -73,6 +74,7 @@ struct lsf_ctx {
     int n_events;
     long long launches;          // kernels launched on behalf of this ctx
     std::mutex ai_mu;            // guards cfg.ai_scale / ai_shift (lsf_set_color_transform may run concurrently with a batch)
+    int grow_bits_hint;          // see Dims::grow_used_bits; 0 until a batch has been counted
     bool last_src_valid;         // LSF_TAP_IMAGE: the frames of the last batch are still where last_src points
     std::string err;
 };
@@ -101,6 +103,8 @@ inline int fail(lsf_ctx *ctx, int code, const std::string &msg)
 // helpers defined in lsf_api.cu
 int stage_in(lsf_ctx *ctx, size_t bytes);              // ctx->seg_in scratch of at least `bytes`
 int ensure_knn(lsf_ctx *ctx, int nq, int nm, int k);   // ctx->knn_scratch for a (nq x nm, k) search
-void mark(lsf_ctx *ctx, const char *name);             // timing event on ctx->st
+void mark(lsf_ctx *ctx, const char *name);
+void lane_filter_destroy(lsf_ctx *ctx);                // lsf_map_exchange.cu
+void exchange_destroy(lsf_ctx *ctx);             // timing event on ctx->st
 cudaMemcpyKind out_kind(int mem);
 template <typename T> inline cudaError_t dalloc(T **p, size_t count) { return cudaMalloc((void **)p, (count ? count : 1) * sizeof(T)); }

@@ -41,7 +41,7 @@ __device__ __forceinline__ int hamming256(const uint4 &qa, const uint4 &qb, cons
 
 // sort key of a candidate: (distance << 17) | discovery key (s* 4 bits | k* 5 bits | xor byte 8 bits); 0 in index order
 constexpr int KEY_SHIFT = 17;
-__device__ __noinline__ int mih_key(const uint4 &qa, const uint4 &qb, const uint4 &a, const uint4 &b)
+__device__ __forceinline__ int mih_key(const uint4 qa, const uint4 qb, const uint4 a, const uint4 b)
 {
     const u32 x[8] = {qa.x ^ a.x, qa.y ^ a.y, qa.z ^ a.z, qa.w ^ a.w, qb.x ^ b.x, qb.y ^ b.y, qb.z ^ b.z, qb.w ^ b.w};
     int best = 9, key = 0;
@@ -95,6 +95,9 @@ __global__ void __launch_bounds__(KT) k_knn_partial(const uint4 *__restrict__ q,
 #pragma unroll
         for (int j = 0; j < K; ++j) { bd[u][j] = 0x7fffffff; bi[u][j] = -1; }
     }
+    int wd[QPT];                       // distance a candidate must not exceed to enter the list (kept in a register)
+#pragma unroll
+    for (int u = 0; u < QPT; ++u) wd[u] = max_dist;
     for (int t0 = m0; t0 < m1; t0 += KTILE) {
         const int nt = min(KTILE, m1 - t0);
         __syncthreads();
@@ -106,9 +109,12 @@ __global__ void __launch_bounds__(KT) k_knn_partial(const uint4 *__restrict__ q,
 #pragma unroll
             for (int u = 0; u < QPT; ++u) {
                 const int dd = hamming256(qa[u], qb[u], a, b);
-                if (dd <= (bd[u][K - 1] >> KEY_SHIFT) && dd <= max_dist) {       // rare: may enter the list
+                if (dd <= wd[u]) {       // rare: may enter the list
                     const int key = (dd << KEY_SHIFT) | (tie_order ? 0 : mih_key(qa[u], qb[u], a, b));
-                    if (key < bd[u][K - 1]) knn_insert<K>(bd[u], bi[u], key, t0 + j);
+                    if (key < bd[u][K - 1]) {
+                        knn_insert<K>(bd[u], bi[u], key, t0 + j);
+                        wd[u] = min(max_dist, bd[u][K - 1] >> KEY_SHIFT);
+                    }
                 }
             }
         }

@@ -186,7 +186,8 @@ struct Prof { long long t_total, t_grow, t_wait, t_rect, t_refine; int grows, ro
 #else
 #define GPROF(...)
 #endif
-constexpr int FAT_WORDS = 40;   // [idx x8][angle(deg) x8][cos x8][sin x8][g2 x8], neighbours row-major, centre skipped
+constexpr int FAT_WORDS = LSD_FAT_WORDS;   // 32 words = one 128-byte line: [idx x8][angle(deg) x8][cos x8][sin x8], neighbours row-major,
+                                           // centre skipped (g2 of accepted pixels is fetched in bulk once a region is worth a rectangle)
 constexpr int RING = 16;        // queue entries whose fat record can be resident at once
 constexpr int SEED_SLOTS = 16;  // seed candidates of a batch of 32 whose fat record is fetched ahead (most are USED already)
 constexpr float kDEG2RADf = (float)kDEG2RAD, k3_2PIf = (float)k3_2PI, k2PIf = (float)k2PI;
@@ -309,7 +310,6 @@ __device__ int grow(const Img &im, GrowSm &sm, Prof &pr, int seed, float seed_de
             if (ni != LSD_NONE && !is_used<SB>(im, ni)) {
                 idx = (int)ni;
                 deg = __uint_as_float(rec[8 + j]); c = __uint_as_float(rec[16 + j]); s = __uint_as_float(rec[24 + j]);
-                g2 = rec[32 + j];
                 xy = sm.qxy[slot] + (u32)nd;
                 // a visit that may be accepted: start pulling its fat record towards L2 now (the queue is short, the
                 // cp.async issued at acceptance would otherwise pay the full DRAM latency one round later)
@@ -394,6 +394,18 @@ __device__ __forceinline__ void seq_add3(Seq3 &sm, int cnt, double ta, double tb
 #define SEQ_RESULT(acc, A, B, C) do { A = __shfl_sync(FULL, acc, 0); B = __shfl_sync(FULL, acc, 1); C = __shfl_sync(FULL, acc, 2); } while (0)
 
 __device__ __forceinline__ double entry_w(const uint4 &e) { return sqrt((double)e.z / 4.0); }   // modgrad
+
+// g2 (squared gradient norm, the weight of a region point) is not part of the neighbour records: once a region is large
+// enough to be fitted, the lanes fetch it for all its points at once (independent gathers, off the growing chain)
+__device__ __forceinline__ void fill_g2(const Img &im, int nreg)
+{
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < nreg; i += 32) {
+        const u32 idx = im.reg[i].x;
+        im.reg[i].z = im.pix[idx].g2;
+    }
+    __syncwarp();
+}
 
 // ---- rectangle fit ------------------------------------------------------------------------------------
 __device__ void region2rect(const Img &im, Seq3 &sm, int nreg, double reg_angle, double prec, double p, Rect &r)
@@ -495,6 +507,7 @@ __device__ bool refine(const Img &im, GrowSm &gsm, Prof &pr, int &nreg, double &
     double tau = 2.0 * sqrt((s_sum - 2.0 * mean * sum) / cnt + mean * mean);
     nreg = grow<SB>(im, gsm, pr, seed, __uint_as_float(se.w), se.z, se.y, seed_c, seed_s, seed_rec, tau, reg_angle);
     if (nreg < 2) return false;
+    fill_g2(im, nreg);
     region2rect(im, sm, nreg, reg_angle, prec, p, rec);
     double density = rect_density(nreg, rec);
     if (density < density_th) {
@@ -828,7 +841,7 @@ __global__ void __launch_bounds__(256) k_lsd_index(Dims d, const LsdWord *__rest
                 if (pp[u] < n) {
                     u32 *rec = out + (size_t)pp[u] * FAT_WORDS + j;
                     rec[0] = r[u] >= 0 ? (u32)r[u] : LSD_NONE;
-                    rec[8] = t[u].x; rec[16] = t[u].y; rec[24] = t[u].z; rec[32] = t[u].w;
+                    rec[8] = t[u].x; rec[16] = t[u].y; rec[24] = t[u].z;
                 }
             }
             // merge with the already visited neighbours.  NW-N, N-NE and W-NW are neighbours of each other (merged at
@@ -995,6 +1008,10 @@ __global__ void __launch_bounds__(32, GROW_PER_SM) k_lsd_grow(Dims d, const LsdW
         setup_img(im, d, img, lsdw, pix, pxy, fat, reg, pixcount);
         im.reg += off;                    // region list of this component (scratch half = +pixcap stays inside the image's buffer)
         im.used = SB ? reinterpret_cast<u32 *>(smraw + sizeof(GrowSm)) : used_global + (size_t)img * used_words;
+        if (SB && im.n > used_words * 32) {       // the bitmap was sized from the previous batch: tell the host, which redoes the batch
+            if (lane == 0) atomicMax(&flags[5], im.n);
+            continue;
+        }
         const float2 *seedcs = scs + (size_t)img * d.pixcap;
         const u32 *ord = corder_ + (size_t)img * d.pixcap + off;
         const u32 *opos = cpos_ + (size_t)img * d.pixcap + off;
@@ -1054,6 +1071,7 @@ __global__ void __launch_bounds__(32, GROW_PER_SM) k_lsd_grow(Dims d, const LsdW
                 double reg_angle;
                 int nreg = grow<SB>(im, sm, pr, seed, __uint_as_float(sdeg), sg2, sxy, sc, ss, srec, prec, reg_angle);
                 if (nreg < min_reg) continue;
+                fill_g2(im, nreg);
                 Rect rec;
                 GPROF(long long t0 = clock64());
                 region2rect(im, sm.seq, nreg, reg_angle, prec, p, rec);
@@ -1152,7 +1170,7 @@ __global__ void __launch_bounds__(128) k_lsd_emit(Dims d, const int *__restrict_
     if (tid == 0) segcount[img] = s_cnt;
 }
 
-void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st)
+void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st, cudaEvent_t ev_indexed)
 {
     static PerDevice tabs, attr;
     tabs.ensure(1, [] {
@@ -1166,11 +1184,14 @@ void launch_lsd_core(const Dims &d, Buffers &b, cudaStream_t st)
     k_lsd_index<<<nimg, 256, 0, st>>>(d, b.lsdw, b.pix, b.pxy, b.pixcount, b.g2max, b.fat, b.order, b.scs, b.label, b.csize, b.coff,
                                       b.corder, b.cpos, b.tasks, b.worklist, wl_cap, b.taskctr, b.candcount);
     ++g_launches;
+    if (ev_indexed) cudaEventRecord(ev_indexed, st);      // timing split: seed order / records / components | growing
     // USED bitmap: shared memory when it fits (the normal case), the global fallback buffer otherwise
-    const int used_words = (d.pixcap + 31) / 32;
+    int used_words = (d.pixcap + 31) / 32;
+    if (d.grow_used_bits > 0 && d.grow_used_bits < d.pixcap && !getenv("LSF_FORCE_GLOBAL_USED")) used_words = (d.grow_used_bits + 31) / 32;
     size_t smem = sizeof(GrowSm) + (size_t)used_words * 4;
     u32 *used_global = nullptr;
     if (smem > 200 * 1024 || getenv("LSF_FORCE_GLOBAL_USED")) {
+        used_words = (d.pixcap + 31) / 32;
         smem = sizeof(GrowSm); used_global = b.usedbits;
         cudaMemsetAsync(b.usedbits, 0, (size_t)nimg * used_words * sizeof(u32), st);
     }

@@ -65,6 +65,7 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     ctx->map = nullptr; ctx->map_n = 0; ctx->map_cap = 0;
     ctx->map_ground = nullptr; ctx->map_color = nullptr; ctx->map_frame = nullptr; ctx->pose_dev = nullptr; ctx->pose_cap = 0;
     memset(&ctx->ex, 0, sizeof(ctx->ex));
+    ctx->lane_filter = nullptr;
     ctx->ex.world = 0;
     ctx->knn_scratch = nullptr; ctx->knn_scratch_cap = 0;
     ctx->tap_tmp = nullptr; ctx->tap_cap = 0;
@@ -138,7 +139,7 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     CKC(dalloc(&b.prectr, 64));
     CKC(dalloc(&b.pix, n * 3 * ctx->pixcap));
     CKC(dalloc(&b.pxy, n * 3 * ctx->pixcap));
-    CKC(dalloc(&b.fat, n * 3 * ctx->pixcap * 40));
+    CKC(dalloc(&b.fat, n * 3 * ctx->pixcap * LSD_FAT_WORDS));
     CKC(dalloc(&b.scs, n * 3 * ctx->pixcap));
     CKC(dalloc(&b.usedbits, n * 3 * (size_t)((ctx->pixcap + 31) / 32)));
     CKC(dalloc(&b.order, n * 3 * ctx->pixcap));
@@ -166,17 +167,17 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     CKC(dalloc(&b.o_ground, oc * 4)); CKC(dalloc(&b.o_keep, oc)); CKC(dalloc(&b.o_desc, oc * 32));
     CKC(dalloc(&b.o_frame, oc));
     b.o_midx = nullptr; b.o_mdist = nullptr;
-    CKC(cudaMallocHost((void **)&ctx->h_small, (n * 3 + n + 1 + 4) * sizeof(int)));
+    CKC(cudaMallocHost((void **)&ctx->h_small, (n * 3 + n + 1 + 8 + n * 3) * sizeof(int)));
     CKC(cudaMemsetAsync(b.flags, 0, 8 * sizeof(int), ctx->st));
     CKC(cudaStreamSynchronize(ctx->st));
     ctx->launches = 0;
     ctx->last_src_valid = false;
+    ctx->grow_bits_hint = 0;
     *out = ctx;
     return LSF_OK;
 #undef CKC
 }
 
-void exchange_destroy(lsf_ctx *ctx);
 
 extern "C" void lsf_destroy(lsf_ctx *ctx)
 {
@@ -191,6 +192,7 @@ extern "C" void lsf_destroy(lsf_ctx *ctx)
     if (ctx->stage_buf[1]) cudaFree(ctx->stage_buf[1]);
     if (ctx->kept_rec) cudaFree(ctx->kept_rec);
     exchange_destroy(ctx);
+    lane_filter_destroy(ctx);
     for (void *p : {(void *)ctx->map_ground, (void *)ctx->map_color, (void *)ctx->map_frame, (void *)ctx->pose_dev}) if (p) cudaFree(p);
     for (int i = 0; i < 2; ++i) if (ctx->staged[i].ev) cudaEventDestroy(ctx->staged[i].ev);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
@@ -406,6 +408,7 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
     for (int i = 0; i < 3; ++i) if (ctx->cp.ai_scale[i] != 1.f || ctx->cp.ai_shift[i] != 0.f) d.identity_color = 0;
 
     d.f0 = 0; d.grow_per_sm = 0;
+    d.grow_used_bits = ctx->grow_bits_hint;
     ctx->n_events = 0;
     mark(ctx, "start");
     int chunk = ctx->cfg.chunk_frames;
@@ -493,7 +496,8 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
         }
         Dims dc = d;
         dc.n = nc; dc.f0 = f0;
-        dc.grow_per_sm = piped ? grow_piped : 0;
+        dc.grow_per_sm = piped ? grow_piped : ctx->cfg.grow_warps_per_sm;
+        if (getenv("LSF_GROW_PER_SM")) dc.grow_per_sm = atoi(getenv("LSF_GROW_PER_SM"));
         Buffers bc = b;
         const size_t i0 = (size_t)3 * f0;
         bc.planesA += (size_t)f0 * PA_COUNT * ps; bc.planesB += (size_t)f0 * PB_COUNT * ps;
@@ -501,7 +505,7 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
         bc.preact += i0 * (size_t)((d.sh + 7) / 8) * d.swp; bc.prectr += c;
         bc.prepatch += i0 * (size_t)((d.sh + 7) / 8) * d.swp * 81;
         bc.lsdw += i0 * d.sh * d.swp; bc.pix += i0 * d.pixcap; bc.pxy += i0 * d.pixcap; bc.scs += i0 * d.pixcap;
-        bc.fat += i0 * d.pixcap * 40; bc.order += i0 * d.pixcap; bc.reg += i0 * 2 * d.pixcap;
+        bc.fat += i0 * d.pixcap * LSD_FAT_WORDS; bc.order += i0 * d.pixcap; bc.reg += i0 * 2 * d.pixcap;
         bc.usedbits += i0 * (size_t)((d.pixcap + 31) / 32);
         bc.pixcount += i0; bc.g2max += i0; bc.cand += i0 * d.segcap; bc.candcount += i0;
         bc.label += i0 * d.pixcap; bc.csize += i0 * d.pixcap; bc.coff += i0 * d.pixcap; bc.corder += i0 * d.pixcap;
@@ -514,7 +518,14 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
         MARK("hysteresis_dilate");
         launch_lsd_pre(dc, bc.planesB, bc, cs);
         MARK("lsd_pre");
-        launch_lsd_core(dc, bc, cs);
+        if (!piped) {      // single stream: time the indexing kernel and the growing kernel separately
+            if (ctx->n_events == (int)ctx->events.size()) { StageTime s; s.name = "lsd_index"; cudaEventCreate(&s.ev); ctx->events.push_back(s); }
+            ctx->events[ctx->n_events].name = "lsd_index";
+            launch_lsd_core(dc, bc, cs, ctx->events[ctx->n_events].ev);
+            ++ctx->n_events;
+        } else {
+            launch_lsd_core(dc, bc, cs);
+        }
         MARK("lsd_grow");
         if (describe) {
             launch_gray_sobel(dc, bc.gray, b.dx + (size_t)f0 * N * 2, nullptr, cs);
@@ -548,10 +559,22 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
     int *hs = ctx->h_small;
     CK(cudaMemcpyAsync(hs, b.segcount, (size_t)n * 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaMemcpyAsync(hs + n * 3, b.frame_off, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaMemcpyAsync(hs + n * 3 + n + 1, b.flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(hs + n * 3 + n + 1, b.flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(hs + n * 3 + n + 1 + 8, b.pixcount, (size_t)n * 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     CK(cudaGetLastError());
     const int *flags = hs + n * 3 + n + 1;
+    {   // size the USED bitmap of the next batch's growing warps from what this batch held (+50 %, at least 4096 pixels)
+        int maxn = 0;
+        for (int i = 0; i < n * 3; ++i) maxn = std::max(maxn, hs[n * 3 + n + 1 + 8 + i]);
+        const int had = ctx->grow_bits_hint;
+        ctx->grow_bits_hint = std::min(ctx->pixcap, std::max(4096, ((maxn + maxn / 2 + 1023) / 1024) * 1024));
+        if (flags[5] && had > 0) {
+            // an image outgrew the bitmap sized from the previous batch (scene change): redo this batch with the new size
+            ctx->grow_bits_hint = std::min(ctx->pixcap, std::max(ctx->grow_bits_hint, ((flags[5] + flags[5] / 2 + 1023) / 1024) * 1024));
+            return lsf_front_end_batch(ctx, bgr, n, src_h, src_w, pitch, mem_kind, stages, k, out);
+        }
+    }
     if (flags[0]) return fail(ctx, LSF_E_CAPACITY, "LSD support pixels of one colour image = " + std::to_string(flags[0]) +
                                                        " exceed max_pixels_per_color = " + std::to_string(ctx->pixcap));
     if (flags[1]) return fail(ctx, LSF_E_CAPACITY, "segments of one colour image = " + std::to_string(flags[1]) +

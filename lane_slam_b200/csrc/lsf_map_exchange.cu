@@ -349,3 +349,118 @@ extern "C" int lsf_odometry_step(lsf_odometry *st, double stamp_nsecs, double ve
     st->theta = ang + rot;
     return 1;
 }
+
+// ---- histogram lane filter ------------------------------------------------------------------------------
+// numpy's pairwise summation of n elements as a plan: leaves (<= 128 elements) and the order their sums are combined in
+static void pairwise_plan(int off, int n, LaneFilterPlan &pl, int &result_leaf)
+{
+    if (n <= 128) {
+        result_leaf = pl.nleaf;
+        pl.leaf_off[pl.nleaf] = (short)off; pl.leaf_len[pl.nleaf] = (short)n;
+        ++pl.nleaf;
+        return;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    int a = 0, b = 0;
+    pairwise_plan(off, n2, pl, a);
+    pairwise_plan(off + n2, n - n2, pl, b);
+    pl.comb_a[pl.ncomb] = (unsigned char)a; pl.comb_b[pl.ncomb] = (unsigned char)b;
+    ++pl.ncomb;
+    result_leaf = a;
+}
+
+struct LaneFilterState {
+    LaneFilterPlan pl;
+    double *d_grid, *phi_grid, *sin_phi, *w_d, *w_phi, *belief, *belief0, *dvw, *est;
+    int *hist;
+    int frames_cap;
+};
+
+static void lane_filter_free(lsf_ctx *ctx)
+{
+    LaneFilterState *s = (LaneFilterState *)ctx->lane_filter;
+    if (!s) return;
+    for (void *p : {(void *)s->d_grid, (void *)s->phi_grid, (void *)s->sin_phi, (void *)s->w_d, (void *)s->w_phi, (void *)s->belief, (void *)s->belief0,
+                    (void *)s->dvw, (void *)s->est, (void *)s->hist})
+        if (p) cudaFree(p);
+    delete s;
+    ctx->lane_filter = nullptr;
+}
+
+void lane_filter_destroy(lsf_ctx *ctx) { lane_filter_free(ctx); }
+
+extern "C" int lsf_lane_filter_init(lsf_ctx *ctx, const lsf_lane_filter_config *c)
+{
+    if (!ctx || !c) return LSF_E_ARG;
+    const long long nc = (long long)c->nd * c->nphi;
+    if (c->nd < 1 || c->nphi < 1 || nc > 1024 || c->r_d < 0 || c->r_phi < 0 || c->r_d > 64 || c->r_phi > 64 || !(c->delta_d > 0) || !(c->delta_phi > 0) ||
+        !c->d_grid || !c->phi_grid || !c->sin_phi || !c->w_d || !c->w_phi || !c->belief0)
+        return fail(ctx, LSF_E_CONFIG, "lsf_lane_filter_init: bad histogram geometry (at most 1024 cells) or missing table");
+    ENTER(ctx);
+    lane_filter_free(ctx);
+    LaneFilterState *s = new LaneFilterState();
+    memset(s, 0, sizeof(*s));
+    ctx->lane_filter = s;
+    LaneFilterPlan &pl = s->pl;
+    pl.nd = c->nd; pl.nphi = c->nphi; pl.r_d = c->r_d; pl.r_phi = c->r_phi;
+    pl.d_min = c->d_min; pl.d_max = c->d_max; pl.phi_min = c->phi_min; pl.phi_max = c->phi_max; pl.delta_d = c->delta_d; pl.delta_phi = c->delta_phi;
+    int root = 0;
+    pairwise_plan(0, (int)nc, pl, root);
+    auto up = [&](double **dst, const double *src, size_t n) -> cudaError_t {
+        cudaError_t e = cudaMalloc((void **)dst, n * sizeof(double));
+        return e != cudaSuccess ? e : cudaMemcpyAsync(*dst, src, n * sizeof(double), cudaMemcpyHostToDevice, ctx->st);
+    };
+    CK(up(&s->d_grid, c->d_grid, nc)); CK(up(&s->phi_grid, c->phi_grid, nc)); CK(up(&s->sin_phi, c->sin_phi, nc));
+    CK(up(&s->w_d, c->w_d, c->r_d + 1)); CK(up(&s->w_phi, c->w_phi, c->r_phi + 1));
+    CK(up(&s->belief0, c->belief0, nc)); CK(up(&s->belief, c->belief0, nc));
+    CK(cudaStreamSynchronize(ctx->st));
+    return LSF_OK;
+}
+
+extern "C" int lsf_lane_filter_reset(lsf_ctx *ctx)
+{
+    if (!ctx || !ctx->lane_filter) return LSF_E_ARG;
+    ENTER(ctx);
+    LaneFilterState *s = (LaneFilterState *)ctx->lane_filter;
+    CK(cudaMemcpyAsync(s->belief, s->belief0, (size_t)s->pl.nd * s->pl.nphi * sizeof(double), cudaMemcpyDeviceToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return LSF_OK;
+}
+
+extern "C" int lsf_lane_filter_batch(lsf_ctx *ctx, const double *dt_v_w, int use_propagation, double *estimates)
+{
+    if (!ctx || !estimates || (use_propagation && !dt_v_w)) return LSF_E_ARG;
+    LaneFilterState *s = (LaneFilterState *)ctx->lane_filter;
+    if (!s) return fail(ctx, LSF_E_ARG, "lsf_lane_filter_batch: call lsf_lane_filter_init first");
+    if (!ctx->have_batch || !(ctx->last_stages & LSF_STAGE_GROUND))
+        return fail(ctx, LSF_E_ARG, "lsf_lane_filter_batch: the last batch must have run LSF_STAGE_GROUND");
+    ENTER(ctx);
+    const int n = ctx->d.n, nc = s->pl.nd * s->pl.nphi;
+    if (n > s->frames_cap) {
+        for (void *p : {(void *)s->dvw, (void *)s->est, (void *)s->hist}) if (p) cudaFree(p);
+        s->dvw = s->est = nullptr; s->hist = nullptr; s->frames_cap = 0;
+        CK(cudaMalloc((void **)&s->dvw, (size_t)n * 3 * sizeof(double))); CK(cudaMalloc((void **)&s->est, (size_t)n * 3 * sizeof(double)));
+        CK(cudaMalloc((void **)&s->hist, (size_t)n * nc * sizeof(int)));
+        s->frames_cap = n;
+    }
+    if (use_propagation) CK(cudaMemcpyAsync(s->dvw, dt_v_w, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemsetAsync(s->hist, 0, (size_t)n * nc * sizeof(int), ctx->st));
+    launch_lane_votes(ctx->cam, ctx->last_S, s->pl.delta_d, s->pl.delta_phi, s->pl.nd, s->pl.nphi, ctx->b, s->hist, ctx->st);
+    launch_lane_filter(s->pl, n, use_propagation ? 1 : 0, s->dvw, s->hist, s->d_grid, s->phi_grid, s->sin_phi, s->w_d, s->w_phi, s->belief, s->est,
+                       ctx->st);
+    CK(cudaMemcpyAsync(estimates, s->est, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaGetLastError());
+    return LSF_OK;
+}
+
+extern "C" int lsf_lane_filter_belief(lsf_ctx *ctx, double *belief)
+{
+    if (!ctx || !belief || !ctx->lane_filter) return LSF_E_ARG;
+    ENTER(ctx);
+    LaneFilterState *s = (LaneFilterState *)ctx->lane_filter;
+    CK(cudaMemcpyAsync(belief, s->belief, (size_t)s->pl.nd * s->pl.nphi * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return LSF_OK;
+}

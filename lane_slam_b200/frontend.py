@@ -87,7 +87,7 @@ class FrontEnd:
     def __init__(self, configuration=None, img_size=(120, 160), top_cutoff=40, camera=None, homography=None,
                  src_size=(480, 640), max_batch=1, device=0, ai_scale=(1, 1, 1), ai_shift=(0, 0, 0),
                  max_segments_per_color=0, max_pixels_per_color=0, max_segments_per_frame=1024, pinned=False,
-                 chunk_frames=0, tie_order=_lib.TIES_REFERENCE):
+                 chunk_frames=0, tie_order=_lib.TIES_REFERENCE, grow_warps_per_sm=0):
         self._lib = _lib.load()
         conf = check_detector_configuration(configuration if configuration is not None
                                             else DEFAULT_DETECTOR_CONFIGURATION)
@@ -123,6 +123,7 @@ class FrontEnd:
         cfg.max_pixels_per_color = int(max_pixels_per_color)
         cfg.device = int(device)
         cfg.chunk_frames = int(chunk_frames)   # 0 auto, < 0 one stream (per-kernel timings), > 0 frames per pipeline chunk
+        cfg.grow_warps_per_sm = int(grow_warps_per_sm)   # 0 = default; fewer when several contexts share the GPU
         cfg.tie_order = int(tie_order)         # order of equal-distance neighbours: the reference's (Mihasher) or ascending index
         self.cfg = cfg
         self.img_size, self.top_cutoff, self.max_batch = tuple(img_size), int(top_cutoff), int(max_batch)

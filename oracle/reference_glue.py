@@ -349,3 +349,66 @@ def map_transform(ground, frame_ids, poses, pose_frame_base=0):
             out[i, o] = (c * px - s * py) + x
             out[i, o + 1] = (s * px + c * py) + y
     return out
+
+
+class LaneFilterHistogram(object):
+    """src/lane_filter/include/lane_filter/lane_filter.py:12-120 restated (same numpy / scipy calls, no ROS): initialize,
+    predict, update (votes via lane_filter_votes above), getEstimate, getMax."""
+    DEFAULTS = dict(mean_d_0=0, mean_phi_0=0, sigma_d_0=0.1, sigma_phi_0=0.1, delta_d=0.02, delta_phi=0.1, d_max=0.3, d_min=-0.15,
+                    phi_min=-1.5, phi_max=1.5, cov_v=0.5, linewidth_white=0.05, linewidth_yellow=0.025, lanewidth=0.23, min_max=0.1,
+                    sigma_d_mask=1.0, sigma_phi_mask=2.0)
+
+    def __init__(self, configuration=None):
+        for k, v in dict(self.DEFAULTS, **(configuration or {})).items():
+            setattr(self, k, v)
+        self.d, self.phi = np.mgrid[self.d_min:self.d_max:self.delta_d, self.phi_min:self.phi_max:self.delta_phi]   # :38
+        self.mean_0 = [self.mean_d_0, self.mean_phi_0]
+        self.cov_0 = [[self.sigma_d_0, 0], [0, self.sigma_phi_0]]
+        self.cov_mask = [self.sigma_d_mask, self.sigma_phi_mask]
+        self.initialize()
+
+    def initialize(self):  # :114-120
+        from scipy.stats import multivariate_normal
+        pos = np.empty(self.d.shape + (2,))
+        pos[:, :, 0] = self.d
+        pos[:, :, 1] = self.phi
+        self.belief = multivariate_normal(self.mean_0, self.cov_0).pdf(pos)
+
+    def predict(self, dt, v, w):  # :47-72
+        from math import floor
+        from scipy.ndimage import gaussian_filter
+        d_t = self.d + v * dt * np.sin(self.phi)
+        phi_t = self.phi + w * dt
+        p_belief = np.zeros(self.belief.shape)
+        for i in range(self.belief.shape[0]):
+            for j in range(self.belief.shape[1]):
+                if self.belief[i, j] > 0:
+                    if d_t[i, j] > self.d_max or d_t[i, j] < self.d_min or phi_t[i, j] < self.phi_min or phi_t[i, j] > self.phi_max:
+                        continue
+                    i_new = int(floor((d_t[i, j] - self.d_min) / self.delta_d))
+                    j_new = int(floor((phi_t[i, j] - self.phi_min) / self.delta_phi))
+                    p_belief[i_new, j_new] += self.belief[i, j]
+        s_belief = np.zeros(self.belief.shape)
+        gaussian_filter(p_belief, self.cov_mask, output=s_belief, mode='constant')
+        if np.sum(s_belief) == 0:
+            return
+        self.belief = s_belief / np.sum(s_belief)
+
+    def update(self, ground, colors):  # :75-102
+        counts = lane_filter_votes(ground, colors, self.delta_d, self.delta_phi).astype(np.float64)
+        if np.linalg.norm(counts) == 0:
+            return None
+        ml = counts / np.sum(counts)
+        self.belief = np.multiply(self.belief, ml)
+        if np.sum(self.belief) == 0:
+            self.belief = ml
+        else:
+            self.belief = self.belief / np.sum(self.belief)
+        return ml
+
+    def getEstimate(self):  # :104-109
+        maxids = np.unravel_index(self.belief.argmax(), self.belief.shape)
+        return [self.d_min + (maxids[0] + 0.5) * self.delta_d, self.phi_min + (maxids[1] + 0.5) * self.delta_phi]
+
+    def getMax(self):
+        return self.belief.max()

@@ -69,6 +69,23 @@ def main():
         out["color_%d" % k] = np.asarray(o["color"], np.uint8)
         out["likelihood_%d" % k] = np.zeros(flt.d.shape) if ml is None else ml
     out["seeds"] = np.array(seeds)
+    # the whole filter, as LaneFilterNode.processSegments drives it (lane_filter_node.py:53-65), over a 24-frame sequence
+    flt.initialize()
+    frames = synth.sequence(24, base_seed=60)
+    rng = np.random.default_rng(4)
+    dvw = np.stack([rng.uniform(0.05, 0.15, 24), rng.uniform(0.0, 0.4, 24), rng.uniform(-1.5, 1.5, 24)], axis=1)
+    est = np.zeros((24, 3))
+    out["filter_belief0"] = flt.belief.copy()
+    for t in range(24):
+        o = cm.front_end_frame(frames[t], cfg, (480, 640), 0, rg.DEFAULT_CAMERA, rg.DEFAULT_HOMOGRAPHY)
+        flt.predict(dt=float(dvw[t, 0]), v=float(dvw[t, 1]), w=float(dvw[t, 2]))
+        flt.update([Segment(c, g) for c, g in zip(o["color"], o["ground"])])
+        d_max, phi_max = flt.getEstimate()
+        est[t] = [d_max, phi_max, flt.getMax()]
+        if t in (0, 11, 23):
+            out["filter_belief_%d" % t] = flt.belief.copy()
+    out["filter_dvw"] = dvw
+    out["filter_estimates"] = est
     np.savez_compressed(os.path.join(HERE, "lane_filter_votes.npz"), **out)
     print("wrote lane_filter_votes.npz:", {k: int(out["likelihood_%d" % k].astype(bool).sum()) for k in range(len(seeds))})
 

@@ -652,3 +652,38 @@ def test_exchange_two_ranks_nccl(mods):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                           "--master-port", "29541", script], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "replay multirank ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_lane_filter_belief_chain(mods):
+    """SURVEY 8f row 2, whole filter: LaneFilterB200.process_batch (one kernel walking the frames of the batch: predict,
+    update, estimate) == the reference's LaneFilterHistogram (golden) and the restated oracle: estimates, belief maximum and
+    the full belief histogram bit for bit; state carried across batches; use_propagation = False path."""
+    import os
+    L, cm, rg, synth, cfg = mods
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lane_filter_votes.npz"))
+    frames = synth.sequence(24, base_seed=60)
+    fe, cam, Hg = _front_end(L, rg, (480, 640), 0, 480, 640, 16)
+    lf = L.LaneFilterB200(dict(L.lane_filter.DEFAULT_CONFIGURATION), fe)
+    assert np.array_equal(lf.belief, g["filter_belief0"])
+    dvw = g["filter_dvw"]
+    est = []
+    for lo, hi in ((0, 12), (12, 24)):                     # two batches: the belief is carried on the device
+        fe.process(frames[lo:hi], stages=L.STAGE_DETECT | L.STAGE_GROUND)
+        est.append(lf.process_batch(dvw[lo:hi, 0], dvw[lo:hi, 1], dvw[lo:hi, 2]))
+        assert np.array_equal(lf.belief, g["filter_belief_%d" % (hi - 1)])
+    est = np.concatenate(est)
+    assert np.array_equal(est, g["filter_estimates"])
+    assert lf.getEstimate() == g["filter_estimates"][23, :2].tolist() and lf.getMax() == g["filter_estimates"][23, 2]
+    # without propagation, against the restated oracle
+    lf.initialize()
+    ref = rg.LaneFilterHistogram()
+    b = fe.process(frames[:8], stages=L.STAGE_DETECT | L.STAGE_GROUND)
+    e2 = lf.process_batch()
+    for t in range(8):
+        gseg = b.frame(t)
+        ref.update(gseg["ground"], gseg["color"])
+        assert e2[t].tolist() == ref.getEstimate() + [ref.getMax()]
+    assert np.array_equal(lf.belief, ref.belief)
+    with pytest.raises(ValueError):
+        L.LaneFilterB200(dict(L.lane_filter.DEFAULT_CONFIGURATION, bogus=1), fe)
+    fe.close()

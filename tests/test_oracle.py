@@ -289,3 +289,19 @@ def test_live_compiled_reference_when_present():
         ri, rd = rn.knn_match(q, m, k)
         oi, od = cm.knn_mihasher(q, m, k)
         assert np.array_equal(ri, oi) and np.array_equal(rd, od)
+
+
+def test_golden_lane_filter_belief_chain():
+    """predict / update / getEstimate / getMax of the restated filter == the reference's LaneFilterHistogram driven over a
+    24-frame sequence (golden from tests/golden/make_golden_lane_filter.py), bit for bit."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lane_filter_votes.npz"))
+    f = rg.LaneFilterHistogram()
+    assert np.array_equal(f.belief, g["filter_belief0"])
+    frames = synth.sequence(24, base_seed=60)
+    for t in range(24):
+        o = cm.front_end_frame(frames[t], CFG, (480, 640), 0, rg.DEFAULT_CAMERA, rg.DEFAULT_HOMOGRAPHY)
+        f.predict(*g["filter_dvw"][t])
+        f.update(o["ground"], o["color"])
+        assert f.getEstimate() + [f.getMax()] == g["filter_estimates"][t].tolist()
+        if t in (0, 11, 23):
+            assert np.array_equal(f.belief, g["filter_belief_%d" % t])
