@@ -224,3 +224,18 @@ def knn_mihasher(q, m, k):
     idx = np.empty((len(q), k), np.int32); dist = np.empty((len(q), k), np.int32)
     lib().orc_knn_mihasher(_p(q), len(q), _p(m), len(m), int(k), _p(idx), _p(dist))
     return idx, dist
+
+
+def jpeg_decode(data):
+    """Baseline JPEG -> BGR uint8 [H,W,3] exactly like cv2.imdecode(data, cv2.IMREAD_COLOR) (libjpeg-turbo defaults: islow
+    IDCT, fancy upsampling); duckietown_utils/jpg.py:21-31.  Raises ValueError for streams outside the restated scope."""
+    buf = np.ascontiguousarray(np.frombuffer(bytes(data), np.uint8) if not isinstance(data, np.ndarray) else data, np.uint8)
+    W, H, nc = C.c_int(), C.c_int(), C.c_int()
+    rc = lib().orc_jpeg_info(_p(buf), C.c_size_t(len(buf)), C.byref(W), C.byref(H), C.byref(nc))
+    if rc != 0:
+        raise ValueError("not a baseline JPEG (%d)" % rc)
+    out = np.empty((H.value, W.value, 3), np.uint8)
+    rc = lib().orc_jpeg_decode_bgr(_p(buf), C.c_size_t(len(buf)), _p(out))
+    if rc != 0:
+        raise ValueError("JPEG decode failed (%d)" % rc)
+    return out

@@ -305,3 +305,27 @@ def test_golden_lane_filter_belief_chain():
         assert f.getEstimate() + [f.getMax()] == g["filter_estimates"][t].tolist()
         if t in (0, 11, 23):
             assert np.array_equal(f.belief, g["filter_belief_%d" % t])
+
+
+def test_jpeg_oracle_equals_cv2_imdecode():
+    """The restated baseline JPEG decode (islow IDCT, fancy upsampling, fixed-point YCbCr) == cv2.imdecode (libjpeg-turbo) bit
+    for bit: the reference's real frames and re-encoded synthetic frames (subsamplings, qualities, restart intervals, odd sizes)."""
+    for i in range(realset.count()):
+        assert np.array_equal(cm.jpeg_decode(realset.jpeg(i)), realset.image(i)), i
+    n = 0
+    for (H, W) in [(480, 640), (123, 161), (97, 203)]:
+        im = synth.frame(5, H, W)
+        for q in (40, 90):
+            for ss in (cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444,
+                       cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440):
+                for rst in (0, 5):
+                    ok, enc = cv2.imencode('.jpg', im, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, ss,
+                                                        cv2.IMWRITE_JPEG_RST_INTERVAL, rst])
+                    assert np.array_equal(cm.jpeg_decode(enc), cv2.imdecode(enc, cv2.IMREAD_COLOR)), (H, W, q, ss, rst)
+                    n += 1
+    ok, enc = cv2.imencode('.jpg', cv2.cvtColor(synth.frame(1), cv2.COLOR_BGR2GRAY))
+    assert np.array_equal(cm.jpeg_decode(enc), cv2.imdecode(enc, cv2.IMREAD_COLOR))
+    ok, enc = cv2.imencode('.jpg', synth.frame(1), [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    with pytest.raises(ValueError):
+        cm.jpeg_decode(enc)
+    assert n == 48
