@@ -176,6 +176,16 @@ LSF_API int lsf_capacities(const lsf_ctx *ctx, int *max_segments_per_color, int 
 LSF_API int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int src_h, int src_w, size_t pitch,
                                 int mem_kind, int stages, int k, lsf_segments *out);
 
+/* Same as lsf_front_end_batch for frames that are still JPEG files -- what the node receives: sensor_msgs/CompressedImage,
+ * decoded by image_cv_from_jpg = cv2.imdecode(..., IMREAD_COLOR) (src/duckietown/include/duckietown_utils/jpg.py:21-31, called at
+ * line_detector_node.py:155).  blob holds the n files back to back (host memory, pinned for an asynchronous copy), file i =
+ * bytes [offsets[i], offsets[i+1]).  The files cross PCIe compressed and are decoded on the GPU, bit-identical to cv2.imdecode
+ * (libjpeg-turbo defaults: islow IDCT, fancy chroma upsampling, fixed-point YCbCr->BGR).  Scope: baseline Huffman JPEG, 8 bit,
+ * 1 or 3 components, sampling factors <= 2 (4:4:4, 4:2:2, 4:4:0, 4:2:0, gray), no restart intervals, all frames of a batch
+ * the same size and sampling; anything else -> LSF_E_ARG (the reference logs and skips undecodable frames,
+ * line_detector_node.py:154-158: decode such a frame on the host and use lsf_front_end_batch). */
+LSF_API int lsf_front_end_batch_jpeg(lsf_ctx *ctx, const uint8_t *blob, const int64_t *offsets, int n, int stages, int k, lsf_segments *out);
+
 /* Streaming replay: start the host->device copy of the NEXT batch of host frames now (returns immediately; the copy
  * runs on the ctx's copy stream into the spare staging buffer) so that it overlaps the kernels of the batch being
  * processed.  A following lsf_front_end_batch call with the same `bgr` pointer and geometry consumes the staged

@@ -47,7 +47,7 @@ class LsfOdometry(C.Structure):
 _EXPORTS = [
     "lsf_map_append", "lsf_map_append_records", "lsf_map_read", "lsf_match_batch", "lsf_odometry_init", "lsf_odometry_step",
     "lsf_nccl_unique_id", "lsf_exchange_init", "lsf_allgather_segments", "lsf_exchange_wait",
-    "lsf_lane_filter_init", "lsf_lane_filter_reset", "lsf_lane_filter_batch", "lsf_lane_filter_belief",
+    "lsf_front_end_batch_jpeg", "lsf_lane_filter_init", "lsf_lane_filter_reset", "lsf_lane_filter_batch", "lsf_lane_filter_belief",
     "lsf_default_config", "lsf_create", "lsf_destroy", "lsf_last_error", "lsf_set_color_transform", "lsf_set_chunk_frames",
     "lsf_set_tie_order", "lsf_capacities", "lsf_cancel_prefetch",
     "lsf_front_end_batch", "lsf_prefetch_batch", "lsf_detect_batch", "lsf_describe_batch", "lsf_project_filter_batch",
@@ -87,6 +87,7 @@ def load():
     lib.lsf_cancel_prefetch.argtypes = [vp]
     lib.lsf_front_end_batch.argtypes = [vp, vp, i32, i32, i32, sz, i32, i32, i32, C.POINTER(LsfSegments)]
     lib.lsf_prefetch_batch.argtypes = [vp, vp, i32, i32, i32, sz]
+    lib.lsf_front_end_batch_jpeg.argtypes = [vp, vp, vp, i32, i32, i32, C.POINTER(LsfSegments)]
     lib.lsf_detect_batch.argtypes = [vp, vp, i32, i32, i32, sz, i32, C.POINTER(LsfSegments)]
     lib.lsf_describe_batch.argtypes = [vp, C.POINTER(LsfSegments)]
     lib.lsf_project_filter_batch.argtypes = [vp, vp, vp, i32, i32, vp, vp]

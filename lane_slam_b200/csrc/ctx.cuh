@@ -34,6 +34,8 @@ struct lsf_ctx {
     int *map_frame;       // [map_cap] global frame id the line was seen in (-1: added through lsf_map_add)
     int map_n, map_cap;
     void *lane_filter;    // LaneFilterState (lsf_map_exchange.cu), or NULL
+    void *jpeg;           // JpegState (k_jpeg.cu), or NULL
+    long long jpeg_last_bytes;   // compressed bytes copied to the device by the last lsf_front_end_batch_jpeg
     double *pose_dev; int pose_cap;   // {x, y, cos, sin} per frame, staging of lsf_map_append_records
     // exchange step (lsf_exchange_init / lsf_allgather_segments / lsf_exchange_wait)
     struct Exchange {
@@ -105,6 +107,7 @@ int stage_in(lsf_ctx *ctx, size_t bytes);              // ctx->seg_in scratch of
 int ensure_knn(lsf_ctx *ctx, int nq, int nm, int k);   // ctx->knn_scratch for a (nq x nm, k) search
 void mark(lsf_ctx *ctx, const char *name);
 void lane_filter_destroy(lsf_ctx *ctx);                // lsf_map_exchange.cu
-void exchange_destroy(lsf_ctx *ctx);             // timing event on ctx->st
+void exchange_destroy(lsf_ctx *ctx);
+void jpeg_destroy(lsf_ctx *ctx);                       // k_jpeg.cu             // timing event on ctx->st
 cudaMemcpyKind out_kind(int mem);
 template <typename T> inline cudaError_t dalloc(T **p, size_t count) { return cudaMalloc((void **)p, (count ? count : 1) * sizeof(T)); }

@@ -224,6 +224,36 @@ class FrontEnd:
             arrays = a
         return SegmentBatch(n, S, arrays, kk)
 
+    def process_jpeg(self, blob, offsets, stages=STAGE_DETECT | STAGE_GROUND, k=0):
+        """Frames that are still JPEG files (sensor_msgs/CompressedImage.data): blob = uint8 array holding the files back to
+        back (pin it for an asynchronous copy), offsets = int64 [n+1].  Decoded on the GPU exactly like cv2.imdecode (jpg.py:21-31)."""
+        blob = np.ascontiguousarray(blob, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        n = len(offsets) - 1
+        while True:
+            a = self._host_arrays()
+            seg = LsfSegments()
+            seg.mem, seg.capacity = MEM_HOST, self._cap
+            for name in ("counts", "frame_offset", "color", "lines_px", "normals", "centers", "pixels_normalized",
+                         "normal_f32", "ground", "keep", "desc", "match_idx", "match_dist"):
+                setattr(seg, name, a[name].ctypes.data)
+            kk = int(k) if (stages & (STAGE_MATCH | STAGE_MATCH_PREV)) else 0
+            rc = self._lib.lsf_front_end_batch_jpeg(self._ctx, blob.ctypes.data, offsets.ctypes.data, n, int(stages), kk, C.byref(seg))
+            if rc == _lib.LSF_E_CAPACITY and seg.n_segments > self._cap and self._cap < self.max_output_rows:
+                self._cap = min(self.max_output_rows, int(seg.n_segments * 1.25) + 64)
+                self._host = None
+                continue
+            self._check(rc)
+            break
+        self._last_frames = None
+        self._last_n = n
+        S = seg.n_segments
+        if kk and kk != 8:
+            arrays = dict(a, match_idx=a["match_idx"].reshape(-1)[:S * kk].reshape(S, kk), match_dist=a["match_dist"].reshape(-1)[:S * kk].reshape(S, kk))
+        else:
+            arrays = a
+        return SegmentBatch(n, S, arrays, kk)
+
     def prefetch(self, frames):
         """Streaming replay: start copying the NEXT batch of host frames (numpy uint8 [n,H,W,3], ideally pinned) to the
         device now; a later process() call with the same array consumes the staged copy (lsf_prefetch_batch)."""

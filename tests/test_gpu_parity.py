@@ -687,3 +687,51 @@ def test_lane_filter_belief_chain(mods):
     with pytest.raises(ValueError):
         L.LaneFilterB200(dict(L.lane_filter.DEFAULT_CONFIGURATION, bogus=1), fe)
     fe.close()
+
+
+def test_jpeg_input_decoded_on_gpu_equals_cv2(mods):
+    """frames arrive as JPEG files (CompressedImage), cross PCIe compressed and are decoded on the GPU --
+    the decoded pixels equal cv2.imdecode (what duckietown_utils/jpg.py does) bit for bit, so every downstream result
+    equals the raw-frame path: the reference's 28 real frames, then other samplings / gray; unsupported flavours are refused."""
+    import cv2
+    import realset
+    L, cm, rg, synth, cfg = mods
+    n = realset.count()
+    blobs = [np.asarray(realset.jpeg(i)) for i in range(n)]
+    off = np.concatenate([[0], np.cumsum([len(b) for b in blobs])]).astype(np.int64)
+    blob = np.concatenate(blobs)
+    st = L.STAGE_DETECT | L.STAGE_GROUND | L.STAGE_DESCRIBE | L.STAGE_MATCH_PREV
+    fe, cam, Hg = _front_end(L, rg, (480, 640), 0, 480, 640, n)
+    frames = np.stack([realset.image(i) for i in range(n)])
+    fe.reset_sequence()
+    ref = _snapshot(fe.process(frames, stages=st, k=2))
+    for _ in range(2):
+        fe.reset_sequence()
+        b = fe.process_jpeg(blob, off, stages=st, k=2)
+        for i in range(n):
+            assert np.array_equal(fe.tap("image", i), frames[i]), "decoded frame %d differs from cv2.imdecode" % i
+        assert _same(ref, _snapshot(b))
+    fe.close()
+    # other flavours, one batch each (same size and sampling inside a batch)
+    im = [synth.frame(s) for s in range(3)]
+    for params in ([cv2.IMWRITE_JPEG_QUALITY, 60, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444],
+                   [cv2.IMWRITE_JPEG_QUALITY, 97, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422],
+                   [cv2.IMWRITE_JPEG_QUALITY, 85, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440], "gray"):
+        enc = [cv2.imencode('.jpg', cv2.cvtColor(x, cv2.COLOR_BGR2GRAY) if params == "gray" else x, [] if params == "gray" else params)[1].ravel() for x in im]
+        off = np.concatenate([[0], np.cumsum([len(e) for e in enc])]).astype(np.int64)
+        fe, cam, Hg = _front_end(L, rg, (480, 640), 0, 480, 640, 3)
+        fe.process_jpeg(np.concatenate(enc), off, stages=L.STAGE_DETECT)
+        for i in range(3):
+            assert np.array_equal(fe.tap("image", i), cv2.imdecode(enc[i], cv2.IMREAD_COLOR)), (params, i)
+        fe.close()
+    # odd size (no TMA path, ragged MCUs)
+    small = synth.frame(4, 123, 161)
+    enc = cv2.imencode('.jpg', small, [cv2.IMWRITE_JPEG_QUALITY, 90])[1].ravel()
+    fe, cam, Hg = _front_end(L, rg, (123, 161), 0, 123, 161, 1)
+    fe.process_jpeg(enc, np.array([0, len(enc)], np.int64), stages=L.STAGE_DETECT)
+    assert np.array_equal(fe.tap("image", 0), cv2.imdecode(enc, cv2.IMREAD_COLOR))
+    with pytest.raises(L.LsfError) as e:
+        prog = cv2.imencode('.jpg', small, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])[1].ravel()
+        fe.process_jpeg(prog, np.array([0, len(prog)], np.int64), stages=L.STAGE_DETECT)
+    assert e.value.code == -2
+    fe.close()
