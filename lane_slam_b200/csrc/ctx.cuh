@@ -35,6 +35,7 @@ struct lsf_ctx {
     int map_n, map_cap;
     void *lane_filter;    // LaneFilterState (lsf_map_exchange.cu), or NULL
     void *jpeg;           // JpegState (k_jpeg.cu), or NULL
+    bool events_keep;     // lsf_front_end_batch_jpeg: the batch continues the timing events of the decode stage
     long long jpeg_last_bytes;   // compressed bytes copied to the device by the last lsf_front_end_batch_jpeg
     double *pose_dev; int pose_cap;   // {x, y, cos, sin} per frame, staging of lsf_map_append_records
     // exchange step (lsf_exchange_init / lsf_allgather_segments / lsf_exchange_wait)

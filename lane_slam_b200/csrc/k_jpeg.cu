@@ -157,41 +157,51 @@ __device__ __forceinline__ size_t plane_off(const jd::Image &g, int c)
     return o;
 }
 
-__global__ void __launch_bounds__(128) k_jpeg_idct(jd::Image g, int n, const int16_t *__restrict__ coef_all, size_t coef_per_img,
+// 8 threads per block: thread j runs the column pass on column j, the 8 x 8 intermediate goes through shared memory (rows padded
+// to 9 words), then the row pass on row j and one 8-byte store.  256 threads = 32 blocks per CTA.
+__global__ void __launch_bounds__(256) k_jpeg_idct(jd::Image g, int n, const int16_t *__restrict__ coef_all, size_t coef_per_img,
                                                   const u16 *__restrict__ qtabs, u8 *__restrict__ plane_all, size_t plane_per_img)
 {
+    __shared__ int ws[32][8][9];
     const int nblocks = g.mcux * g.mcuy * g.bpm;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)n * nblocks) return;
-    const int img = (int)(gid / nblocks);
-    int tt = (int)(gid - (long long)img * nblocks);
-    // enumerate blocks plane by plane (neighbouring threads write neighbouring blocks of a plane row)
-    int c = 0;
-    while (c < g.ncomp - 1 && tt >= g.bw[c] * g.bh[c]) { tt -= g.bw[c] * g.bh[c]; ++c; }
-    const int by = tt / g.bw[c], bx = tt - by * g.bw[c];
-    int slot0 = 0;
-    for (int k = 0; k < c; ++k) slot0 += g.hs[k] * g.vs[k];
-    const int mcu = (by / g.vs[c]) * g.mcux + (bx / g.hs[c]);
-    const int slot = slot0 + (by % g.vs[c]) * g.hs[c] + (bx % g.hs[c]);
-    const int16_t *cf = coef_all + (size_t)img * coef_per_img + ((size_t)mcu * g.bpm + slot) * 64;
-    __align__(16) int16_t cc[64];
-    {
-        const uint4 *p = reinterpret_cast<const uint4 *>(cf);
+    const int j = threadIdx.x & 7, lb = threadIdx.x >> 3;
+    const long long gid = (long long)blockIdx.x * 32 + lb;
+    const bool ok = gid < (long long)n * nblocks;
+    int img = 0, c = 0, by = 0, bx = 0;
+    const int16_t *cf = coef_all;
+    if (ok) {
+        img = (int)(gid / nblocks);
+        int tt = (int)(gid - (long long)img * nblocks);
+        // enumerate blocks plane by plane (neighbouring groups write neighbouring blocks of a plane row)
+        while (c < g.ncomp - 1 && tt >= g.bw[c] * g.bh[c]) { tt -= g.bw[c] * g.bh[c]; ++c; }
+        by = tt / g.bw[c]; bx = tt - by * g.bw[c];
+        int slot0 = 0;
+        for (int k = 0; k < c; ++k) slot0 += g.hs[k] * g.vs[k];
+        const int mcu = (by / g.vs[c]) * g.mcux + (bx / g.hs[c]);
+        const int slot = slot0 + (by % g.vs[c]) * g.hs[c] + (bx % g.hs[c]);
+        cf = coef_all + (size_t)img * coef_per_img + ((size_t)mcu * g.bpm + slot) * 64;
+        const u16 *q = qtabs + ((size_t)img * 3 + c) * 64;
+        int o[8];
+        jd::idct_1d(cf[j] * __ldg(q + j), cf[8 + j] * __ldg(q + 8 + j), cf[16 + j] * __ldg(q + 16 + j), cf[24 + j] * __ldg(q + 24 + j),
+                    cf[32 + j] * __ldg(q + 32 + j), cf[40 + j] * __ldg(q + 40 + j), cf[48 + j] * __ldg(q + 48 + j), cf[56 + j] * __ldg(q + 56 + j), o);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) reinterpret_cast<uint4 *>(cc)[i] = p[i];
+        for (int r = 0; r < 8; ++r) ws[lb][r][j] = jd::descale(o[r], 11);
     }
-    __align__(16) u16 q[64];
-    {
-        const uint4 *p = reinterpret_cast<const uint4 *>(qtabs + ((size_t)img * 3 + c) * 64);
+    __syncwarp();
+    if (ok) {
+        const int *w = ws[lb][j];
+        int o[8];
+        jd::idct_1d(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], o);
+        u32 lo = 0, hi = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) reinterpret_cast<uint4 *>(q)[i] = __ldg(p + i);
+        for (int k = 0; k < 4; ++k) {
+            lo |= (u32)jd::range_limit(jd::descale(o[k], 18)) << (8 * k);
+            hi |= (u32)jd::range_limit(jd::descale(o[4 + k], 18)) << (8 * k);
+        }
+        const int stride = g.bw[c] * 8;
+        u8 *dst = plane_all + (size_t)img * plane_per_img + plane_off(g, c) + ((size_t)by * 8 + j) * stride + bx * 8;
+        *reinterpret_cast<uint2 *>(dst) = make_uint2(lo, hi);
     }
-    __align__(16) u8 o[64];
-    jd::idct_block(cc, q, o, 8);
-    const int stride = g.bw[c] * 8;
-    u8 *dst = plane_all + (size_t)img * plane_per_img + plane_off(g, c) + ((size_t)by * 8) * stride + bx * 8;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) *reinterpret_cast<uint2 *>(dst + (size_t)r * stride) = reinterpret_cast<const uint2 *>(o)[r];
 }
 
 __global__ void __launch_bounds__(256) k_jpeg_color(jd::Image g, int n, const u8 *__restrict__ plane_all, size_t plane_per_img,
@@ -224,6 +234,53 @@ __global__ void __launch_bounds__(256) k_jpeg_color(jd::Image g, int n, const u8
     } else {
         for (int i = 0; i < 4 && x0 + i < W; ++i) { dst[3 * i] = out[3 * i]; dst[3 * i + 1] = out[3 * i + 1]; dst[3 * i + 2] = out[3 * i + 2]; }
     }
+}
+
+// 4:2:0, 8 pixels per thread (W % 8 == 0): the six vertical sums 3 * near + far of each chroma plane are formed once and shared
+// by the eight pixels; aligned word loads for luma and chroma, three 8-byte stores.
+__global__ void __launch_bounds__(256) k_jpeg_color_420(jd::Image g, int n, const u8 *__restrict__ plane_all, size_t plane_per_img,
+                                                       u8 *__restrict__ bgr, size_t frame_bytes)
+{
+    const int W = g.W, H = g.H, W8 = W / 8;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)n * H * W8) return;
+    const int img = (int)(gid / ((long long)H * W8));
+    const int rem = (int)(gid - (long long)img * H * W8);
+    const int y = rem / W8, x0 = (rem - y * W8) * 8;
+    const u8 *pl = plane_all + (size_t)img * plane_per_img;
+    const int ys = g.bw[0] * 8, cs = g.bw[1] * 8;
+    const int dw = (W + 1) / 2, dh = (H + 1) / 2;
+    const int sy = y >> 1, sx = x0 >> 1;
+    int ny = (y & 1) ? sy + 1 : sy - 1;
+    ny = ny < 0 ? 0 : (ny > dh - 1 ? dh - 1 : ny);
+    const uint2 yv = *reinterpret_cast<const uint2 *>(pl + (size_t)y * ys + x0);
+    int col[2][6];       // vertical sums of chroma columns sx-1 .. sx+4 (edge columns are only used inside the image)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const u8 *p = pl + plane_off(g, 1 + c);
+        const u8 *r0 = p + (size_t)sy * cs + sx, *r1 = p + (size_t)ny * cs + sx;
+        const u32 a = *reinterpret_cast<const u32 *>(r0), b = *reinterpret_cast<const u32 *>(r1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) col[c][1 + k] = (int)((a >> (8 * k)) & 0xff) * 3 + (int)((b >> (8 * k)) & 0xff);
+        col[c][0] = sx > 0 ? r0[-1] * 3 + r1[-1] : 0;
+        col[c][5] = sx + 4 < dw ? r0[4] * 3 + r1[4] : 0;
+    }
+    __align__(8) u8 out[24];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int yy = (int)(((i < 4 ? yv.x : yv.y) >> (8 * (i & 3))) & 0xff);
+        const int k = 1 + (i >> 1);
+        int cc[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int cur = col[c][k];
+            if (i & 1) cc[c] = (sx + (i >> 1) + 1 > dw - 1) ? (cur * 4 + 7) >> 4 : (cur * 3 + col[c][k + 1] + 7) >> 4;
+            else cc[c] = (sx + (i >> 1) == 0) ? (cur * 4 + 8) >> 4 : (cur * 3 + col[c][k - 1] + 8) >> 4;
+        }
+        jd::ycc_to_bgr(yy, cc[0], cc[1], out + 3 * i);
+    }
+    uint2 *dst = reinterpret_cast<uint2 *>(bgr + (size_t)img * frame_bytes + ((size_t)y * W + x0) * 3);
+    dst[0] = reinterpret_cast<const uint2 *>(out)[0]; dst[1] = reinterpret_cast<const uint2 *>(out)[1]; dst[2] = reinterpret_cast<const uint2 *>(out)[2];
 }
 
 }  // namespace lsf
@@ -346,6 +403,7 @@ extern "C" int lsf_front_end_batch_jpeg(lsf_ctx *ctx, const uint8_t *blob, const
     memcpy(j->h_tabsets, sets.data(), sets.size() * sizeof(jd::Tabs));
     for (int i = 0; i < n; ++i) memcpy(j->h_qtabs + (size_t)i * 192, imgs[i].q, 192 * sizeof(u16));
     ctx->n_events = 0;
+    mark(ctx, "start");
     cudaStream_t st = ctx->st;
     // the frame buffer the decoded frames go to: the ctx's first staging buffer (nothing may be staged in it)
     if (ctx->staged[0].valid || ctx->staged[1].valid) { CK(cudaStreamSynchronize(ctx->copy_st)); ctx->staged[0].valid = ctx->staged[1].valid = false; }
@@ -357,13 +415,23 @@ extern "C" int lsf_front_end_batch_jpeg(lsf_ctx *ctx, const uint8_t *blob, const
     CK(cudaMemcpyAsync(j->qtabs, j->h_qtabs, (size_t)n * 192 * sizeof(u16), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(j->coef, 0, (size_t)n * j->coef_per_img * sizeof(int16_t), st));
     CK(cudaMemsetAsync(j->status, 0, (size_t)n * sizeof(int), st));
+    mark(ctx, "jpeg_h2d");
     const size_t per_img_words = j->clean_words / (size_t)std::max(n, 1);
     k_jpeg_huff<<<n, JT, 0, st>>>(g, j->blob, j->items, j->tabsets, j->clean, per_img_words, j->coef, j->coef_per_img, j->status);
+    if (getenv("LSF_JPEG_SPLIT_TIMING")) mark(ctx, "jpeg_huffman");
     const long long nblk = (long long)n * g.mcux * g.mcuy * g.bpm;
-    k_jpeg_idct<<<(unsigned)((nblk + 127) / 128), 128, 0, st>>>(g, n, j->coef, j->coef_per_img, j->qtabs, j->plane, j->plane_per_img);
-    const long long npx4 = (long long)n * g.H * ((g.W + 3) / 4);
-    k_jpeg_color<<<(unsigned)((npx4 + 255) / 256), 256, 0, st>>>(g, n, j->plane, j->plane_per_img, frames, frame_bytes);
+    k_jpeg_idct<<<(unsigned)((nblk + 31) / 32), 256, 0, st>>>(g, n, j->coef, j->coef_per_img, j->qtabs, j->plane, j->plane_per_img);
+    if (getenv("LSF_JPEG_SPLIT_TIMING")) mark(ctx, "jpeg_idct");
+    if (g.ncomp == 3 && g.hs[0] == 2 && g.vs[0] == 2 && (g.W & 7) == 0 && (frame_bytes & 7) == 0) {
+        const long long npx8 = (long long)n * g.H * (g.W / 8);
+        k_jpeg_color_420<<<(unsigned)((npx8 + 255) / 256), 256, 0, st>>>(g, n, j->plane, j->plane_per_img, frames, frame_bytes);
+    } else {
+        const long long npx4 = (long long)n * g.H * ((g.W + 3) / 4);
+        k_jpeg_color<<<(unsigned)((npx4 + 255) / 256), 256, 0, st>>>(g, n, j->plane, j->plane_per_img, frames, frame_bytes);
+    }
     g_launches += 3;
+    mark(ctx, "jpeg_decode");
+    ctx->events_keep = true;
     CK(cudaMemcpyAsync(j->h_status, j->status, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaGetLastError());
     ctx->jpeg_last_bytes = (long long)blob_bytes;

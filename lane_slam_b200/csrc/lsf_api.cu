@@ -66,7 +66,7 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     ctx->map_ground = nullptr; ctx->map_color = nullptr; ctx->map_frame = nullptr; ctx->pose_dev = nullptr; ctx->pose_cap = 0;
     memset(&ctx->ex, 0, sizeof(ctx->ex));
     ctx->lane_filter = nullptr;
-    ctx->jpeg = nullptr; ctx->jpeg_last_bytes = 0;
+    ctx->jpeg = nullptr; ctx->jpeg_last_bytes = 0; ctx->events_keep = false;
     ctx->ex.world = 0;
     ctx->knn_scratch = nullptr; ctx->knn_scratch_cap = 0;
     ctx->tap_tmp = nullptr; ctx->tap_cap = 0;
@@ -411,8 +411,8 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
 
     d.f0 = 0; d.grow_per_sm = 0;
     d.grow_used_bits = ctx->grow_bits_hint;
-    ctx->n_events = 0;
-    mark(ctx, "start");
+    if (!ctx->events_keep) { ctx->n_events = 0; mark(ctx, "start"); }
+    ctx->events_keep = false;
     int chunk = ctx->cfg.chunk_frames;
     if (getenv("LSF_CHUNK_FRAMES")) chunk = atoi(getenv("LSF_CHUNK_FRAMES"));
     const bool host_in = mem_kind != LSF_MEM_DEVICE;
