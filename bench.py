@@ -132,12 +132,32 @@ def make_frames(n, base_seed, start=0, h=H, w=W, dense=False):
     return synth.sequence(n, base_seed=base_seed, H=h, W=w, dense=dense, start=start)
 
 
+JPEG_QUALITY = 90
+
+
+def encode_jpeg(frames):
+    """The camera delivers JPEG (sensor_msgs/CompressedImage, decoded by duckietown_utils/jpg.py:21-31 with cv2.imdecode): the
+    synthetic frames are encoded once, outside every timed region (cv2.imencode, quality 90, 4:2:0).  Returns (blob uint8,
+    offsets int64 [n+1])."""
+    import cv2
+    enc = [cv2.imencode(".jpg", f, [cv2.IMWRITE_JPEG_QUALITY, JPEG_QUALITY])[1].ravel() for f in frames]
+    off = np.concatenate([[0], np.cumsum([len(e) for e in enc])]).astype(np.int64)
+    return np.concatenate(enc), off
+
+
+def decode_jpeg(blob, off):
+    import cv2
+    return np.stack([cv2.imdecode(blob[off[i]:off[i + 1]], cv2.IMREAD_COLOR) for i in range(len(off) - 1)])
+
+
 def workload_config(frames_per_gpu):
     """The `config` object of the JSON line: identical for the GPU arm and the reference (CPU) arm -- same generator, same
     seeds (rank r replays synth.sequence(base_seed = r * frames_per_gpu)), same detector configuration and stages."""
     return {"workload": WORKLOAD, "frames_per_step_per_gpu": frames_per_gpu, "img_size": [H, W], "top_cutoff": 0, "k": K_NN,
             "detector": "line_detector_node/default.yaml thresholds", "stages": "detect+ground+sanity+describe+match_prev",
-            "input": "synth.sequence(base_seed = rank * frames_per_step_per_gpu), uint8 BGR", "match_radius": 128,
+            "input": "synth.sequence(base_seed = rank * frames_per_step_per_gpu) as JPEG files (cv2.imencode quality %d, 4:2:0): "
+                     "e2e / reference arm start from the JPEG bytes (decode = cv2.imdecode semantics), `value` from the decoded BGR "
+                     "frames resident in HBM" % JPEG_QUALITY, "match_radius": 128,
             "l2": "inputs 921.6 MB per step exceed the 126 MB L2 (no flush needed)"}
 
 
@@ -149,14 +169,15 @@ def _cpu_worker(args):
     cv2.setNumThreads(1)
     from oracle import cmodel as cm, reference_glue as rg
     start, count = args
-    frames = make_frames(count, 0, start=start)          # frames [start, start + count) of rank 0's sequence
+    blob, off = encode_jpeg(make_frames(count, 0, start=start))     # frames [start, start + count) of rank 0's sequence, as JPEG
     det = rg.LineDetectorLSD(dict(rg.DEFAULT_DETECTOR_CONFIG))
     gp = rg.GroundProjection()
     prev = None
     t0 = time.perf_counter()
     nseg = 0
     for f in range(count):
-        r = rg.front_end_frame(frames[f], det, gp, (H, W), 0)
+        frame = cv2.imdecode(blob[off[f]:off[f + 1]], cv2.IMREAD_COLOR)      # jpg.py:21-31, line_detector_node.py:155
+        r = rg.front_end_frame(frame, det, gp, (H, W), 0)
         gray = cv2.cvtColor(r["image"], cv2.COLOR_BGR2GRAY)
         blur = cv2.GaussianBlur(gray, (5, 5), 1)
         dx = cv2.Sobel(blur, cv2.CV_16S, 1, 0, ksize=3)
@@ -205,8 +226,8 @@ def run_reference(args):
         "config": workload_config(args.frames),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": "%d frames per step = %d contiguous pieces of the same 1000-frame sequence (same seeds), one "
-                                   "single-threaded cv2 worker per core (restated reference glue + cv2 4.13 LSD/Canny, C LBD, "
-                                   "cv2.BFMatcher)" % (total, cores)},
+                                   "single-threaded cv2 worker per core (cv2.imdecode of the JPEG frame + restated reference glue + cv2 4.13 "
+                                   "LSD/Canny, C LBD, cv2.BFMatcher)" % (total, cores)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -279,95 +300,137 @@ def run_gpu(args):
         if rank == 0 and args.verbose:
             print("[bench %.1fs] %s" % (time.perf_counter() - t_start, msg), file=sys.stderr, flush=True)
 
-    frames_np = make_frames(n, base_seed=rank * n)            # this rank's shard of the log
-    log("frames generated")
+    raw_np = make_frames(n, base_seed=rank * n)               # this rank's shard of the log ...
+    blob_np, off = encode_jpeg(raw_np)                        # ... as the JPEG files the camera delivers
+    frames_np = decode_jpeg(blob_np, off)                     # = cv2.imdecode of them: "the frames" of every arm
+    del raw_np
+    log("frames generated, %.1f KB of JPEG per frame" % (off[-1] / n / 1e3))
     pinned = torch.from_numpy(frames_np).pin_memory()
     dev = pinned.cuda(non_blocking=False)
-    fe = L.FrontEnd(dict(L.DEFAULT_DETECTOR_CONFIGURATION), img_size=(H, W), top_cutoff=0, src_size=(H, W), max_batch=n,
-                    device=local, max_segments_per_frame=256, pinned=True)
+    T = max(1, args.inflight)                                 # contexts (= batches) in flight on this GPU, one host thread each
+    fes = [L.FrontEnd(dict(L.DEFAULT_DETECTOR_CONFIGURATION), img_size=(H, W), top_cutoff=0, src_size=(H, W), max_batch=n,
+                      device=local, max_segments_per_frame=256, pinned=True, chunk_frames=(-1 if T > 1 else 0)) for _ in range(T)]
+    fe = fes[0]
+    blobs = [torch.from_numpy(blob_np).pin_memory().numpy() for _ in range(T)]
     stages = L.STAGE_DETECT | L.STAGE_GROUND | L.STAGE_DESCRIBE | L.STAGE_MATCH_PREV
     # the path's one exchange step lives in liblsf.so: one ncclAllGather on the ctx's exchange stream, overlapped with the next step
-    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if world > 1:
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(odometry.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-    fe.exchange_init(rank=rank, world=world, unique_id=bytes(uid.cpu().numpy()) if world > 1 else None)
-    inflight = [0]
-    kept_seen = [0]
-
-    def step(frames):
-        fe.reset_sequence()
-        b = fe.process(frames, stages=stages, k=K_NN)
+    for c in range(T):
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if world > 1:
-            if inflight[0]:                                   # the exchange of the previous step ran under this step's kernels
-                _, ntot, _ = fe.exchange_wait(); inflight[0] -= 1; kept_seen[0] = ntot
-            fe.allgather_start(frame_base=rank * n); inflight[0] += 1
+            if rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(odometry.nccl_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, 0)
+        fes[c].exchange_init(rank=rank, world=world, unique_id=bytes(uid.cpu().numpy()) if world > 1 else None)
+    inflight = [0] * T
+    kept_seen = [0]
+    last = [None] * T
+
+    def step(c, kind):
+        f = fes[c]
+        f.reset_sequence()
+        if kind == "jpeg":
+            b = f.process_jpeg(blobs[c], off, stages=stages, k=K_NN)
+        else:
+            b = f.process(dev if kind == "dev" else pinned.numpy(), stages=stages, k=K_NN)
+        if world > 1:
+            if inflight[c]:                                   # the exchange of this context's previous step ran under this step's kernels
+                _, ntot, _ = f.exchange_wait(); inflight[c] -= 1; kept_seen[0] = ntot
+            f.allgather_start(frame_base=rank * n); inflight[c] += 1
+        last[c] = b
         return b
 
-    def drain():
-        while inflight[0]:
-            _, ntot, _ = fe.exchange_wait(); inflight[0] -= 1; kept_seen[0] = ntot
+    def drain(c):
+        while inflight[c]:
+            _, ntot, _ = fes[c].exchange_wait(); inflight[c] -= 1; kept_seen[0] = ntot
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    ext = torch.cuda.ExternalStream(fe.stream(), device=torch.device("cuda", local))   # the stream liblsf launches on
+    exts = [torch.cuda.ExternalStream(f.stream(), device=torch.device("cuda", local)) for f in fes]   # the streams liblsf launches on
 
-    def timed(frames, steps, stream_ahead=False):
-        """K steps bracketed by barrier + synchronize, timed on the device with CUDA events recorded on the
-        stream the kernels are launched on (the lsf ctx stream); per-stage times come from the library's own
-        events on the same stream.  stream_ahead: host frames are staged one step ahead with fe.prefetch() -- every
-        step's host->device copy is still issued inside the timed region (the first one before the first step).
-        The last step's exchange is finished (lsf_exchange_wait orders the ctx stream behind it) before the closing event.
-        Returns (seconds, per-stage ms, d2h bytes, last batch)."""
+    def timed(kind, steps, ncontexts=T, stream_ahead=False):
+        """K steps bracketed by barrier + synchronize, timed on the device with CUDA events recorded on the streams the kernels are
+        launched on (the lsf ctx streams).  With `ncontexts` > 1 the steps are dealt round robin to that many contexts, each driven
+        by its own host thread, so that consecutive batches overlap on the GPU (the latency-bound LSD search of one under the
+        issue-bound kernels of another; for JPEG input also the host-side header parsing, the H2D copy and the decode).  The
+        last exchange of every context is finished before its closing event.  stream_ahead (raw host frames, one context):
+        fe.prefetch() stages step i+1 while step i computes.  Returns (seconds, per-stage ms of context 0, d2h bytes, last batch)."""
+        import threading
         stage_ms = {}
-        d2h = 0
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record(ext)
-        if stream_ahead:
-            fe.prefetch(frames)
-        for i in range(steps):
-            if stream_ahead and i + 1 < steps:
-                fe.prefetch(frames)
-            b = step(frames)
-            for name, ms in fe.timings():
-                stage_ms[name] = stage_ms.get(name, 0.0) + ms
-            S = b.n_segments
-            d2h = S * (1 + 16 + 16 + 8 + 16 + 8 + 32 + 1 + 32 + 8 * K_NN) + (4 * n + 1) * 4
-        drain()
-        e1.record(ext)
-        barrier()
-        e1.synchronize()
-        dt = e0.elapsed_time(e1) * 1e-3
-        return dt, stage_ms, d2h, b
+        d2h = [0]
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in range(ncontexts)]
+        errors = []
+        start = threading.Barrier(ncontexts + 1)
 
-    log("context ready")
-    # warm-up (>= 3)
-    for i in range(max(3, args.warmup)):
-        b = step(dev)
-        log("warmup %d: S=%d %s" % (i, b.n_segments, ["%s=%.2f" % x for x in fe.timings()]))
-    step(pinned.numpy())
-    drain()
-    log("warmup host path done")
+        def work(c):
+            try:
+                torch.cuda.set_device(local)
+                start.wait()
+                for i in range(c, steps, ncontexts):
+                    if stream_ahead and i + 1 < steps:
+                        fes[c].prefetch(pinned.numpy())
+                    b = step(c, kind)
+                    if c == 0:
+                        for name, ms in fes[0].timings():
+                            stage_ms[name] = stage_ms.get(name, 0.0) + ms
+                        S = b.n_segments
+                        d2h[0] = S * (1 + 16 + 16 + 8 + 16 + 8 + 32 + 1 + 32 + 8 * K_NN) + (4 * n + 1) * 4
+                drain(c)
+                e1[c].record(exts[c])
+            except Exception as e:      # surfaced below
+                errors.append(repr(e))
+                try:
+                    start.abort()
+                except Exception:
+                    pass
+        ths = [threading.Thread(target=work, args=(c,)) for c in range(ncontexts)]
+        for t in ths:
+            t.start()
+        barrier()
+        e0.record(exts[0])
+        if stream_ahead:
+            fes[0].prefetch(pinned.numpy())
+        start.wait()
+        for t in ths:
+            t.join()
+        if errors:
+            raise RuntimeError("bench step failed: %s" % errors)
+        barrier()
+        dt = max(e0.elapsed_time(e) for e in e1) * 1e-3
+        return dt, stage_ms, d2h[0], last[0]
+
+    log("contexts ready")
+    # warm-up (>= 3 per context and input kind)
+    for c in range(T):
+        for i in range(max(3, args.warmup)):
+            b = step(c, "dev")
+        step(c, "jpeg"); step(c, "jpeg")
+        drain(c)
+    step(0, "raw"); drain(0)
+    log("warm-up done: S=%d" % b.n_segments)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = fe.launch_count()
-    dt_dev, _, _, b = timed(dev, args.steps)
-    launches = fe.launch_count() - l0
+    l0 = sum(f.launch_count() for f in fes)
+    dt_dev, _, _, b = timed("dev", args.steps)
+    launches = sum(f.launch_count() for f in fes) - l0
     parity = parity_gate(L, b, frames_np, args.parity_frames) if (rank == 0 and args.parity_frames > 0) else None
     seg_per_step, kept_per_step = int(b.n_segments), int(b.keep.sum())
-    dt_e2e, _, d2h_bytes, b = timed(pinned.numpy(), args.steps, stream_ahead=True)
-    dt_e2e_single, _, _, _ = timed(pinned.numpy(), args.steps)
+    dt_e2e, _, d2h_bytes, bj = timed("jpeg", args.steps)
+    jpeg_same = bool(bj.n_segments == b.n_segments and np.array_equal(bj.lines_px, b.lines_px) and np.array_equal(bj.desc, b.desc))
+    fe.set_chunk_frames(0)                                                         # one batch at a time: chunk pipeline inside the batch
+    step(0, "dev"); step(0, "jpeg"); drain(0)
+    dt_dev1, _, _, _ = timed("dev", args.steps, ncontexts=1)
+    dt_jpeg1, jpeg_stage_ms, _, _ = timed("jpeg", args.steps, ncontexts=1)
+    dt_raw, _, _, _ = timed("raw", args.steps, ncontexts=1, stream_ahead=True)     # round-1 e2e: raw BGR host frames, staged one step ahead
     # per-kernel times for the roofline: same steps on ONE stream (chunk pipeline off) so that the library's
     # CUDA events bracket each kernel; not part of `value` / `e2e`
     fe.set_chunk_frames(-1)
-    step(dev)
-    _, stage_ms, _, _ = timed(dev, args.steps)
+    step(0, "dev")
+    _, stage_ms, _, _ = timed("dev", args.steps, ncontexts=1)
     fe.set_chunk_frames(0)
     clocks = sampler.stop() if rank == 0 else None
     # p50 latency of one frame through the same call (batch = 1, host frame in, segment list out), rank 0 only
@@ -386,6 +449,8 @@ def run_gpu(args):
         lat = {"batch1_p50_ms": float(np.percentile(ts, 50)), "batch1_p95_ms": float(np.percentile(ts, 95)), "frames": int(len(ts)),
                "how": "host wall clock around FrontEnd.process of one pinned host frame (all stages, k=2), after 30 warm-up frames"}
     extra = {}
+    for f in fes[1:]:
+        f.close()
     if "c5" in args.extras:
         extra["c5"] = bench_c5(torch, dist, L, fe, dev, n, rank, world, local, args, log)
     fe.close()
@@ -397,9 +462,9 @@ def run_gpu(args):
         if "c3" in args.extras:
             extra["c3"] = bench_c3(torch, L, local, args, log)
     if world > 1:
-        t = torch.tensor([dt_dev, dt_e2e, dt_e2e_single], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dt_dev, dt_e2e, dt_dev1, dt_jpeg1, dt_raw], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt_dev, dt_e2e, dt_e2e_single = float(t[0]), float(t[1]), float(t[2])
+        dt_dev, dt_e2e, dt_dev1, dt_jpeg1, dt_raw = [float(x) for x in t]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -434,17 +499,25 @@ def run_gpu(args):
         "ms_per_step": 1e3 * dt_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/f64", "data": "synthetic",
         "config": workload_config(n),
-        "pipeline": {"chunks": "device frames: 2 chunks, host frames: 8 chunks over 8 streams (copy of chunk c+1 overlaps kernels of chunk c)",
+        "pipeline": {"contexts_in_flight": T,
+                     "how": "%d contexts per GPU, one host thread each, consecutive steps dealt round robin (batches overlap on the GPU); "
+                            "with several contexts every batch runs on one stream (the chunk pipeline is for one batch at a time)" % T,
+                     "one_batch_at_a_time": {"value": total_frames / dt_dev1, "ms_per_step": 1e3 * dt_dev1 / args.steps,
+                                             "e2e_jpeg_value": total_frames / dt_jpeg1, "e2e_jpeg_ms_per_step": 1e3 * dt_jpeg1 / args.steps},
                      "segments_per_step": seg_per_step, "kept_per_step": kept_per_step,
                      "exchange": None if world == 1 else "lsf_allgather_segments: one ncclAllGather of fixed-capacity slots on the ctx's exchange "
                                                         "stream, started after step i and finished under step i+1 (last one inside the timed region); "
                                                         "%d records gathered per step" % kept_seen[0]},
-        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(n * H * W * 3), "d2h_bytes_per_step": int(d2h_bytes),
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(off[-1]) + n * (16 + 384) + 8192, "d2h_bytes_per_step": int(d2h_bytes),
                 "ms_per_step": 1e3 * dt_e2e / args.steps,
-                "how": "host (pinned) frames through FrontEnd.process; input staging is double-buffered: fe.prefetch() starts the "
-                       "H2D of step i+1 while step i computes (all K copies inside the timed region, the first not overlapped); "
-                       "segment lists copied back every step",
-                "single_call_value": total_frames / dt_e2e_single, "single_call_ms_per_step": 1e3 * dt_e2e_single / args.steps},
+                "how": "the frames as JPEG files in pinned host memory through FrontEnd.process_jpeg (lsf_front_end_batch_jpeg): every step "
+                       "parses the headers, copies the compressed bytes to the device, decodes them on the GPU (bit-identical to "
+                       "cv2.imdecode), runs the whole front end and copies the segment lists back, all inside the timed region",
+                "jpeg_bytes_per_frame": float(off[-1]) / n, "jpeg_quality": JPEG_QUALITY,
+                "same_result_as_value_arm": jpeg_same,
+                "decode_stage_ms_per_step": {k: v / args.steps for k, v in jpeg_stage_ms.items() if k.startswith("jpeg")},
+                "raw_bgr": {"value": total_frames / dt_raw, "ms_per_step": 1e3 * dt_raw / args.steps, "h2d_bytes_per_step": int(n * H * W * 3),
+                            "how": "round-1 definition: decoded BGR frames in pinned host memory, H2D staged one step ahead (PCIe-bound)"}},
         "gpu_launches": int(launches),
         "latency": dict(lat, batch1000_ms_per_frame_amortised=1e3 * dt_dev / args.steps / n,
                         batch1000_step_ms=1e3 * dt_dev / args.steps) if lat else None,
@@ -603,6 +676,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--verbose", action="store_true", help="progress on stderr")
     ap.add_argument("--parity-frames", type=int, default=64, help="frames of the timed step re-checked by the CPU oracle (0 = skip)")
+    ap.add_argument("--inflight", type=int, default=2, help="contexts (batches) in flight per GPU, one host thread each")
     ap.add_argument("--extras", default="c3,c4,c5", help="other BASELINE configs measured after the headline (c3, c4: 1 GPU only)")
     ap.add_argument("--c3-batch", type=int, default=256)
     ap.add_argument("--c5-frames", type=int, default=100000, help="length of the replayed log (total over all GPUs)")

@@ -39,24 +39,40 @@ __device__ __forceinline__ int hamming256(const uint4 &qa, const uint4 &qb, cons
     return __popc(ones) + 2 * __popc(twos) + 4 * (__popc(f1) + __popc(f2));
 }
 
-// sort key of a candidate: (distance << 17) | discovery key (s* 4 bits | k* 5 bits | xor byte 8 bits); 0 in index order
+// sort key of a candidate: (distance << 17) | discovery key (s* 4 bits | k* 5 bits | xor byte 8 bits); 0 in index order.
+// The discovery key of (query of lane X, train row) is evaluated by the whole warp: all lanes hold the same train row at
+// the same time, lane L takes byte L of the XOR (the query words of lane X are broadcast with eight shuffles), and one
+// warp-wide minimum of (popcount << 13 | byte index << 8 | byte) is the key.  ~25 warp instructions instead of ~200 per
+// candidate evaluated by a single lane while the other 31 wait.
 constexpr int KEY_SHIFT = 17;
-__device__ __forceinline__ int mih_key(const uint4 qa, const uint4 qb, const uint4 a, const uint4 b)
+__device__ __forceinline__ u32 sel8(const uint4 &a, const uint4 &b, int w)
 {
-    const u32 x[8] = {qa.x ^ a.x, qa.y ^ a.y, qa.z ^ a.z, qa.w ^ a.w, qb.x ^ b.x, qb.y ^ b.y, qb.z ^ b.z, qb.w ^ b.w};
-    int best = 9, key = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        u32 c = x[w] - ((x[w] >> 1) & 0x55555555u);
-        c = (c & 0x33333333u) + ((c >> 2) & 0x33333333u);
-        c = (c + (c >> 4)) & 0x0f0f0f0fu;                     // popcount of every byte
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int pc = (int)((c >> (8 * j)) & 0xffu);
-            if (pc < best) { best = pc; key = (pc << 13) | ((4 * w + j) << 8) | (int)((x[w] >> (8 * j)) & 0xffu); }
-        }
+    const u32 lo = (w & 2) ? ((w & 1) ? a.w : a.z) : ((w & 1) ? a.y : a.x);
+    const u32 hi = (w & 2) ? ((w & 1) ? b.w : b.z) : ((w & 1) ? b.y : b.x);
+    return (w & 4) ? hi : lo;
+}
+// enter: this lane's candidate may enter its list.  Returns this lane's key (valid where enter is set).  Warp-uniform call.
+__device__ __forceinline__ int mih_keys_warp(bool enter, const uint4 &qa, const uint4 &qb, const uint4 &a, const uint4 &b)
+{
+    const int lane = threadIdx.x & 31;
+    unsigned em = __ballot_sync(0xffffffffu, enter);
+    int mykey = 0;
+    if (!em) return 0;
+    const u32 rw = sel8(a, b, lane >> 2);             // the train row's word that holds byte `lane`
+    while (em) {
+        const int X = __ffs(em) - 1;
+        em &= em - 1;
+        uint4 xa, xb;
+        xa.x = __shfl_sync(0xffffffffu, qa.x, X); xa.y = __shfl_sync(0xffffffffu, qa.y, X);
+        xa.z = __shfl_sync(0xffffffffu, qa.z, X); xa.w = __shfl_sync(0xffffffffu, qa.w, X);
+        xb.x = __shfl_sync(0xffffffffu, qb.x, X); xb.y = __shfl_sync(0xffffffffu, qb.y, X);
+        xb.z = __shfl_sync(0xffffffffu, qb.z, X); xb.w = __shfl_sync(0xffffffffu, qb.w, X);
+        const u32 byte = ((sel8(xa, xb, lane >> 2) ^ rw) >> (8 * (lane & 3))) & 0xffu;
+        const u32 packed = ((u32)__popc(byte) << 13) | ((u32)lane << 8) | byte;
+        const u32 kx = __reduce_min_sync(0xffffffffu, packed);
+        if (lane == X) mykey = (int)kx;
     }
-    return key;
+    return mykey;
 }
 
 template <int K>
@@ -74,9 +90,9 @@ __device__ __forceinline__ void knn_insert(int (&bd)[K], int (&bi)[K], int dd, i
 constexpr int QPT = 1;         // queries per thread (2 was measured slower: 0.51 vs 0.42 ms at C4, although the one-query
                                // kernel is MIO-throttled on the tile broadcasts)
 
-template <int K>
+template <int K, bool REFORDER>
 __global__ void __launch_bounds__(KT) k_knn_partial(const uint4 *__restrict__ q, int nq_cap, const int *__restrict__ nq_dev,
-                                                   const uint4 *__restrict__ m, int nm, int max_dist, int tie_order, int chunk,
+                                                   const uint4 *__restrict__ m, int nm, int max_dist, int chunk,
                                                    int *__restrict__ pidx, int *__restrict__ pdist)
 {
     __shared__ uint4 tile[KTILE * 2];
@@ -109,11 +125,14 @@ __global__ void __launch_bounds__(KT) k_knn_partial(const uint4 *__restrict__ q,
 #pragma unroll
             for (int u = 0; u < QPT; ++u) {
                 const int dd = hamming256(qa[u], qb[u], a, b);
-                if (dd <= wd[u]) {       // rare: may enter the list
-                    const int key = (dd << KEY_SHIFT) | (tie_order ? 0 : mih_key(qa[u], qb[u], a, b));
+                const bool enter = dd <= wd[u];       // rare: may enter the list
+                const int dkey = REFORDER ? mih_keys_warp(enter, qa[u], qb[u], a, b) : 0;
+                if (enter) {
+                    const int key = (dd << KEY_SHIFT) | dkey;
                     if (key < bd[u][K - 1]) {
                         knn_insert<K>(bd[u], bi[u], key, t0 + j);
-                        wd[u] = min(max_dist, bd[u][K - 1] >> KEY_SHIFT);
+                        // index order: an equal distance never displaces an earlier row, so the bar can be one lower
+                        wd[u] = min(max_dist, (bd[u][K - 1] >> KEY_SHIFT) - (REFORDER ? 0 : 1));
                     }
                 }
             }
@@ -187,8 +206,10 @@ __global__ void __launch_bounds__(128) k_knn_prev(const uint4 *__restrict__ desc
             for (int j = 0; j < m; ++j) {
                 uint4 a = tile[2 * j], b = tile[2 * j + 1];
                 const int dd = hamming256(qa, qbv, a, b);
-                if (dd <= (bd[K - 1] >> KEY_SHIFT) && dd <= max_dist) {
-                    const int key = (dd << KEY_SHIFT) | (tie_order ? 0 : mih_key(qa, qbv, a, b));
+                const bool enter = dd <= (bd[K - 1] >> KEY_SHIFT) && dd <= max_dist;
+                const int dkey = tie_order ? 0 : mih_keys_warp(enter, qa, qbv, a, b);
+                if (enter) {
+                    const int key = (dd << KEY_SHIFT) | dkey;
                     if (key < bd[K - 1]) knn_insert<K>(bd, bi, key, t0 + j);
                 }
             }
@@ -243,10 +264,10 @@ void launch_knn(const u8 *q, int nq_cap, const int *nq_dev, const u8 *m, int nm,
     dim3 grid((nq_cap + KT * QPT - 1) / (KT * QPT), nsplit);
     const uint4 *q4 = (const uint4 *)q, *m4 = (const uint4 *)m;
     switch (K) {
-    case 1: k_knn_partial<1><<<grid, KT, 0, st>>>(q4, nq_cap, nq_dev, m4, nm, max_dist, tie_order, chunk, pidx, pdist); break;
-    case 2: k_knn_partial<2><<<grid, KT, 0, st>>>(q4, nq_cap, nq_dev, m4, nm, max_dist, tie_order, chunk, pidx, pdist); break;
-    case 4: k_knn_partial<4><<<grid, KT, 0, st>>>(q4, nq_cap, nq_dev, m4, nm, max_dist, tie_order, chunk, pidx, pdist); break;
-    default: k_knn_partial<8><<<grid, KT, 0, st>>>(q4, nq_cap, nq_dev, m4, nm, max_dist, tie_order, chunk, pidx, pdist); break;
+    case 1: (tie_order ? k_knn_partial<1, false> : k_knn_partial<1, true>)<<<grid, KT, 0, st>>>(q4, nq_cap, nq_dev, m4, nm, max_dist, chunk, pidx, pdist); break;
+    case 2: (tie_order ? k_knn_partial<2, false> : k_knn_partial<2, true>)<<<grid, KT, 0, st>>>(q4, nq_cap, nq_dev, m4, nm, max_dist, chunk, pidx, pdist); break;
+    case 4: (tie_order ? k_knn_partial<4, false> : k_knn_partial<4, true>)<<<grid, KT, 0, st>>>(q4, nq_cap, nq_dev, m4, nm, max_dist, chunk, pidx, pdist); break;
+    default: (tie_order ? k_knn_partial<8, false> : k_knn_partial<8, true>)<<<grid, KT, 0, st>>>(q4, nq_cap, nq_dev, m4, nm, max_dist, chunk, pidx, pdist); break;
     }
     ++g_launches;
     k_knn_merge<<<(nq_cap + 127) / 128, 128, 0, st>>>(nq_cap, nq_dev, nsplit, K, k, pidx, pdist, idx, dist);
