@@ -191,7 +191,8 @@ struct Span {
 
 template <typename TabsT>
 JD_FN void decode_span(const uint32_t *words, const TabsT &tabs, const int32_t *slot_dc, const int32_t *slot_ac, int bpm, Span &st,
-                       uint32_t pos_limit, int16_t *coef /* or NULL */, uint32_t u_start, uint32_t max_blocks)
+                       uint32_t pos_limit, int16_t *coef /* or NULL */, uint32_t u_start, uint32_t max_blocks,
+                       int16_t *dcdiff = nullptr /* optional: DC differences go here (one per block) instead of coef[blk * 64] */)
 {
     uint32_t pos = st.pos, s = st.s, adv = st.adv;
     const uint8_t *ZZ = zigzag();
@@ -225,7 +226,10 @@ JD_FN void decode_span(const uint32_t *words, const TabsT &tabs, const int32_t *
             const uint32_t bits = size ? ((v << len) >> (32 - size)) : 0;
             const int32_t val = (size && bits < (1u << (size - 1))) ? (int32_t)bits - (int32_t)(1u << size) + 1 : (int32_t)bits;
             const uint32_t blk = (u_start + adv) >> 6;          // adv counts slots from the span's first block boundary ...
-            if (blk < max_blocks) coef[(size_t)blk * 64 + ZZ[nz]] = (int16_t)val;
+            if (blk < max_blocks) {
+                if (z == 0 && dcdiff) dcdiff[blk] = (int16_t)val;
+                else coef[(size_t)blk * 64 + ZZ[nz]] = (int16_t)val;
+            }
         }
         pos += len + (write ? size : 0);
         uint32_t znext = endblk ? 64 : nz + 1;

@@ -14,7 +14,10 @@
 
 namespace lsf {
 
-constexpr int JT = 512;                  // threads (= subsequences) per image
+#ifndef LSF_JT
+#define LSF_JT 512
+#endif
+constexpr int JT = LSF_JT;               // threads (= subsequences) per image
 
 struct JpegItem {
     u32 ent_off, ent_len;                // entropy-coded bytes inside the blob
@@ -25,6 +28,7 @@ struct JpegState {
     u8 *blob; size_t blob_cap;
     u32 *clean; size_t clean_words;      // per image: stuffing-free big-endian words
     int16_t *coef; size_t coef_per_img;  // per image: nblocks * 64
+    int16_t *dcdiff;                     // per image: nblocks DC differences (decode order)
     u8 *plane; size_t plane_per_img;     // per image: Y, Cb, Cr planes back to back (padded to whole MCUs)
     JpegItem *items, *h_items;
     u16 *qtabs, *h_qtabs;                // [n][3][64]
@@ -53,7 +57,8 @@ __device__ __forceinline__ int block_excl_scan(int v, int *sm, int &total)
 
 __global__ void __launch_bounds__(JT) k_jpeg_huff(jd::Image g, const u8 *__restrict__ blob, const JpegItem *__restrict__ items,
                                                  const jd::Tabs *__restrict__ tabsets, u32 *__restrict__ clean_all, size_t clean_words,
-                                                 int16_t *__restrict__ coef_all, size_t coef_per_img, int *__restrict__ status)
+                                                 int16_t *__restrict__ coef_all, size_t coef_per_img, int16_t *__restrict__ dcdiff_all,
+                                                 int *__restrict__ status)
 {
     __shared__ jd::Tabs tabs;
     __shared__ jd::Span E[2][JT];
@@ -128,22 +133,23 @@ __global__ void __launch_bounds__(JT) k_jpeg_huff(jd::Image g, const u8 *__restr
         jd::Span st;
         if (t == 0) { st.pos = 0; st.s = 0; } else { st.pos = E[cur][t - 1].pos; st.s = E[cur][t - 1].s; }
         st.adv = 0;
-        jd::decode_span(words, tabs, g.slot_dc, g.slot_ac, g.bpm, st, limit, coef, ustart, nblocks);
+        jd::decode_span(words, tabs, g.slot_dc, g.slot_ac, g.bpm, st, limit, coef, ustart, nblocks, dcdiff_all + (size_t)img * (coef_per_img / 64));
     }
     __syncthreads();
     // ---- DC prediction: running sum of the differences per component, in decode order ----
     {
         const int nm = g.mcux * g.mcuy, per = (nm + JT - 1) / JT;
         const int m0 = min(nm, t * per), m1 = min(nm, m0 + per);
+        const int16_t *dd = dcdiff_all + (size_t)img * (coef_per_img / 64);       // DC differences, one per block, decode order
         int sum[3] = {0, 0, 0};
         for (int m = m0; m < m1; ++m)
-            for (int s = 0; s < g.bpm; ++s) sum[g.slot_comp[s]] += coef[((size_t)m * g.bpm + s) * 64];
+            for (int s = 0; s < g.bpm; ++s) sum[g.slot_comp[s]] += dd[m * g.bpm + s];
         int base[3], dummy;
         for (int c = 0; c < 3; ++c) base[c] = block_excl_scan(sum[c], s_scan, dummy);
         for (int m = m0; m < m1; ++m)
             for (int s = 0; s < g.bpm; ++s) {
                 const int c = g.slot_comp[s];
-                base[c] += coef[((size_t)m * g.bpm + s) * 64];
+                base[c] += dd[m * g.bpm + s];
                 coef[((size_t)m * g.bpm + s) * 64] = (int16_t)base[c];
             }
     }
@@ -165,13 +171,12 @@ __global__ void __launch_bounds__(256) k_jpeg_idct(jd::Image g, int n, const int
     __shared__ int ws[32][8][9];
     const int nblocks = g.mcux * g.mcuy * g.bpm;
     const int j = threadIdx.x & 7, lb = threadIdx.x >> 3;
-    const long long gid = (long long)blockIdx.x * 32 + lb;
-    const bool ok = gid < (long long)n * nblocks;
-    int img = 0, c = 0, by = 0, bx = 0;
+    const int img = blockIdx.y;
+    int tt = blockIdx.x * 32 + lb;
+    const bool ok = tt < nblocks;
+    int c = 0, by = 0, bx = 0;
     const int16_t *cf = coef_all;
     if (ok) {
-        img = (int)(gid / nblocks);
-        int tt = (int)(gid - (long long)img * nblocks);
         // enumerate blocks plane by plane (neighbouring groups write neighbouring blocks of a plane row)
         while (c < g.ncomp - 1 && tt >= g.bw[c] * g.bh[c]) { tt -= g.bw[c] * g.bh[c]; ++c; }
         by = tt / g.bw[c]; bx = tt - by * g.bw[c];
@@ -242,10 +247,9 @@ __global__ void __launch_bounds__(256) k_jpeg_color_420(jd::Image g, int n, cons
                                                        u8 *__restrict__ bgr, size_t frame_bytes)
 {
     const int W = g.W, H = g.H, W8 = W / 8;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)n * H * W8) return;
-    const int img = (int)(gid / ((long long)H * W8));
-    const int rem = (int)(gid - (long long)img * H * W8);
+    const int img = blockIdx.y;
+    const int rem = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rem >= H * W8) return;
     const int y = rem / W8, x0 = (rem - y * W8) * 8;
     const u8 *pl = plane_all + (size_t)img * plane_per_img;
     const int ys = g.bw[0] * 8, cs = g.bw[1] * 8;
@@ -291,7 +295,7 @@ void jpeg_destroy(lsf_ctx *ctx)
 {
     JpegState *j = (JpegState *)ctx->jpeg;
     if (!j) return;
-    for (void *p : {(void *)j->blob, (void *)j->clean, (void *)j->coef, (void *)j->plane, (void *)j->items, (void *)j->qtabs, (void *)j->tabsets,
+    for (void *p : {(void *)j->blob, (void *)j->clean, (void *)j->coef, (void *)j->dcdiff, (void *)j->plane, (void *)j->items, (void *)j->qtabs, (void *)j->tabsets,
                     (void *)j->status})
         if (p) cudaFree(p);
     for (void *p : {(void *)j->h_items, (void *)j->h_qtabs, (void *)j->h_tabsets, (void *)j->h_status}) if (p) cudaFreeHost(p);
@@ -311,13 +315,14 @@ static int jpeg_reserve(lsf_ctx *ctx, const jd::Image &g, int n, size_t blob_byt
     size_t plane = 0;
     for (int c = 0; c < g.ncomp; ++c) plane += (size_t)g.bw[c] * g.bh[c] * 64;
     if (n > j->n_cap || g.W != j->W || g.H != j->H || nblocks * 64 > j->coef_per_img || plane > j->plane_per_img) {
-        for (void *p : {(void *)j->coef, (void *)j->plane, (void *)j->items, (void *)j->qtabs, (void *)j->status}) if (p) cudaFree(p);
+        for (void *p : {(void *)j->coef, (void *)j->dcdiff, (void *)j->plane, (void *)j->items, (void *)j->qtabs, (void *)j->status}) if (p) cudaFree(p);
         for (void *p : {(void *)j->h_items, (void *)j->h_qtabs, (void *)j->h_status}) if (p) cudaFreeHost(p);
-        j->coef = nullptr; j->plane = nullptr; j->items = nullptr; j->qtabs = nullptr; j->status = nullptr;
+        j->coef = nullptr; j->dcdiff = nullptr; j->plane = nullptr; j->items = nullptr; j->qtabs = nullptr; j->status = nullptr;
         j->h_items = nullptr; j->h_qtabs = nullptr; j->h_status = nullptr;
         const int cap = std::max(n, ctx->max_batch);
         j->coef_per_img = nblocks * 64; j->plane_per_img = (plane + 15) & ~(size_t)15;
         CK(cudaMalloc((void **)&j->coef, (size_t)cap * j->coef_per_img * sizeof(int16_t)));
+        CK(cudaMalloc((void **)&j->dcdiff, (size_t)cap * (j->coef_per_img / 64) * sizeof(int16_t)));
         CK(cudaMalloc((void **)&j->plane, (size_t)cap * j->plane_per_img));
         CK(cudaMalloc((void **)&j->items, (size_t)cap * sizeof(JpegItem)));
         CK(cudaMalloc((void **)&j->qtabs, (size_t)cap * 3 * 64 * sizeof(u16)));
@@ -417,14 +422,14 @@ extern "C" int lsf_front_end_batch_jpeg(lsf_ctx *ctx, const uint8_t *blob, const
     CK(cudaMemsetAsync(j->status, 0, (size_t)n * sizeof(int), st));
     mark(ctx, "jpeg_h2d");
     const size_t per_img_words = j->clean_words / (size_t)std::max(n, 1);
-    k_jpeg_huff<<<n, JT, 0, st>>>(g, j->blob, j->items, j->tabsets, j->clean, per_img_words, j->coef, j->coef_per_img, j->status);
+    k_jpeg_huff<<<n, JT, 0, st>>>(g, j->blob, j->items, j->tabsets, j->clean, per_img_words, j->coef, j->coef_per_img, j->dcdiff, j->status);
     if (getenv("LSF_JPEG_SPLIT_TIMING")) mark(ctx, "jpeg_huffman");
     const long long nblk = (long long)n * g.mcux * g.mcuy * g.bpm;
-    k_jpeg_idct<<<(unsigned)((nblk + 31) / 32), 256, 0, st>>>(g, n, j->coef, j->coef_per_img, j->qtabs, j->plane, j->plane_per_img);
+    k_jpeg_idct<<<dim3((unsigned)((nblk / n + 31) / 32), n), 256, 0, st>>>(g, n, j->coef, j->coef_per_img, j->qtabs, j->plane, j->plane_per_img);
     if (getenv("LSF_JPEG_SPLIT_TIMING")) mark(ctx, "jpeg_idct");
     if (g.ncomp == 3 && g.hs[0] == 2 && g.vs[0] == 2 && (g.W & 7) == 0 && (frame_bytes & 7) == 0) {
-        const long long npx8 = (long long)n * g.H * (g.W / 8);
-        k_jpeg_color_420<<<(unsigned)((npx8 + 255) / 256), 256, 0, st>>>(g, n, j->plane, j->plane_per_img, frames, frame_bytes);
+        const int npx8 = g.H * (g.W / 8);
+        k_jpeg_color_420<<<dim3((unsigned)((npx8 + 255) / 256), n), 256, 0, st>>>(g, n, j->plane, j->plane_per_img, frames, frame_bytes);
     } else {
         const long long npx4 = (long long)n * g.H * ((g.W + 3) / 4);
         k_jpeg_color<<<(unsigned)((npx4 + 255) / 256), 256, 0, st>>>(g, n, j->plane, j->plane_per_img, frames, frame_bytes);

@@ -718,7 +718,10 @@ __device__ __forceinline__ void setup_img(Img &im, const Dims &d, int img, const
 //            components is fine); tasks appended to the work list (>= BIG_COMP pixels from the front, the others from
 //            the back: long chains start first)
 //   phase 4  stable partition of order[] by task -> corder[] (+ cpos[] = position in order[])
-constexpr int GROW_PER_SM = 16;  // resident growing warps per SM, measured: 12 -> 5.3 ms, 16 -> 4.7 ms, 20 -> 5.8 ms, 28 (72 regs, spills) -> 6.0 ms
+#ifndef LSF_GROW_PER_SM_BUILD
+#define LSF_GROW_PER_SM_BUILD 16
+#endif
+constexpr int GROW_PER_SM = LSF_GROW_PER_SM_BUILD;  // resident growing warps per SM, measured: 12 -> 5.3 ms, 16 -> 4.7 ms, 20 -> 5.8 ms, 28 (72 regs, spills) -> 6.0 ms
 constexpr int MAXC = LSD_MAXC;   // tasks per image: component slot s goes to task s % MAXC (a task = a union of whole components)
 constexpr int BIG_COMP = 768;
 constexpr int SL_MAX = 8192;     // support pixels whose union-find labels fit in shared memory
