@@ -12,6 +12,7 @@ from .frontend import (FrontEnd, SegmentBatch, DEFAULT_DETECTOR_CONFIGURATION, D
                        WHITE, YELLOW, RED, scaled_calibration, check_detector_configuration)
 from .line_detector import LineDetectorB200, Detections, LineDetectorInterface
 from .lane_filter import LaneFilterB200
+from . import wire, odometry, replay
 from .messages import Segment, SegmentList, Vector2D, Point, segment_lists_from_batch
 
 STAGE_ALL = STAGE_DETECT | STAGE_GROUND | STAGE_DESCRIBE

@@ -735,3 +735,51 @@ def test_jpeg_input_decoded_on_gpu_equals_cv2(mods):
         fe.process_jpeg(prog, np.array([0, len(prog)], np.int64), stages=L.STAGE_DETECT)
     assert e.value.code == -2
     fe.close()
+
+
+def test_rosbag_replay_without_ros(mods, tmp_path):
+    """SURVEY 8f row 3, both halves: a rosbag of CompressedImage + WheelsCmdStamped messages is read without ROS, the JPEG
+    frames go to the GPU compressed, the odometry poses place the kept segments in the map, and the three nodes' SegmentList
+    messages come back in the reference's wire layout."""
+    import realset
+    from lane_slam_b200 import wire, odometry
+    L, cm, rg, synth, cfg = mods
+    n = 8
+    msgs = []
+    for i in range(n):
+        h = wire.Header(i, 100 + i // 2, (i % 2) * 500000000, "cam")
+        msgs.append(("/duck/camera_node/image/compressed", "sensor_msgs/CompressedImage", (h.secs, h.nsecs),
+                     wire.serialize_compressed_image(wire.CompressedImage(h, "jpeg", np.asarray(realset.jpeg(i))))))
+        msgs.append(("/duck/wheels_driver_node/wheels_cmd", "duckietown_msgs/WheelsCmdStamped", (h.secs, h.nsecs + 1000),
+                     wire.serialize_wheels_cmd(wire.WheelsCmdStamped(wire.Header(i, h.secs, (i * 100000000) % 1000000000, ""), 0.3, 0.32))))
+    bag = str(tmp_path / "log.bag")
+    wire.write_bag(bag, msgs, compression="bz2", chunk_messages=6)
+    imgs, od, poses = [], odometry.Odometry(0.0), []
+    for topic, typ, t, data in wire.read_bag(bag):
+        if typ == "sensor_msgs/CompressedImage":
+            imgs.append(wire.deserialize_compressed_image(data))
+        else:
+            w = wire.deserialize_wheels_cmd(data)
+            od.getPose(w.header.nsecs, w.vel_left, w.vel_right)
+            poses.append(od.pose())
+    blob, off = wire.jpeg_blob(imgs)
+    fe, cam, Hg = _front_end(L, rg, (480, 640), 0, 480, 640, n)
+    b = fe.process_jpeg(blob, off, stages=L.STAGE_DETECT | L.STAGE_GROUND | L.STAGE_DESCRIBE)
+    fe.map_append(np.array(poses), frame_base=0)
+    assert fe.map_size() == int(b.keep.sum()) > 0
+    for stage in ("detector", "ground", "sanity"):
+        out = wire.serialize_batch(b, stage, headers=[m.header for m in imgs])
+        for f in range(n):
+            h, seg = wire.deserialize_segment_list(out[f])
+            assert h == imgs[f].header
+            g = b.frame(f)
+            sel = g["keep"] if stage == "sanity" else np.ones(len(g["color"]), bool)
+            assert np.array_equal(seg["color"], g["color"][sel])
+            if stage == "detector":
+                assert np.array_equal(seg["pixels_normalized"].reshape(-1, 4), g["pixels_normalized"]) and np.array_equal(seg["normal"], g["normal"])
+            else:
+                assert np.array_equal(seg["points"][:, :, :2].reshape(-1, 4), g["ground"][sel]) and (seg["points"][:, :, 2] == 0).all()
+    # the frames the GPU decoded are the frames cv2 would have decoded
+    o = cm.front_end_frame(realset.image(3), cfg, (480, 640), 0, cam, Hg)
+    assert b.frame(3)["counts"] == o["counts"] and np.array_equal(b.frame(3)["lines_px"], o["lines_px"])
+    fe.close()
