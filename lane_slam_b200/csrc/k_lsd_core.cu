@@ -849,19 +849,15 @@ __global__ void __launch_bounds__(256) k_lsd_index(Dims d, const LsdWord *__rest
             }
             // merge with the already visited neighbours.  NW-N, N-NE and W-NW are neighbours of each other (merged at
             // their own turn), so one merge with N is enough when N exists, at most two otherwise.
+            // (one ballot per pixel batch instead of four shuffles: lanes 0..3 of a group hold NW, N, NE, W and merge themselves;
+            // concurrent unions on the same pixel are fine, the forest is lock-free)
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int rNW = __shfl_sync(FULL, r[u], 0, 8), rN = __shfl_sync(FULL, r[u], 1, 8),
-                          rNE = __shfl_sync(FULL, r[u], 2, 8), rW = __shfl_sync(FULL, r[u], 3, 8);
-                if (j == 0 && pp[u] < n) {
-                    const u32 p = (u32)pp[u];
-                    if (rN >= 0) uf_union(lab, p, (u32)rN);
-                    else {
-                        if (rNE >= 0) uf_union(lab, p, (u32)rNE);
-                        if (rNW >= 0) uf_union(lab, p, (u32)rNW);
-                        else if (rW >= 0) uf_union(lab, p, (u32)rW);
-                    }
-                }
+                const u32 have = (__ballot_sync(FULL, r[u] >= 0) >> (lane & 24)) & 0xfu;    // bit 0 NW, 1 N, 2 NE, 3 W of this group
+                bool mine;
+                if (have & 2u) mine = j == 1;                                        // N exists: it connects all the others
+                else mine = (j == 2 && (have & 4u)) || (j == 0 && (have & 1u)) || (j == 3 && (have & 8u) && !(have & 1u));
+                if (mine && pp[u] < n) uf_union(lab, (u32)pp[u], (u32)r[u]);
             }
         }
     }
