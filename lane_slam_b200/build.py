@@ -40,6 +40,10 @@ def build(force=False, verbose=False):
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = ["-DLSF_GROW_PROF"] if os.environ.get("LSF_GROW_PROF") else []   # developer aid: cycle counters in k_lsd_grow
+    if os.environ.get("LSF_JPEG_PROF"):                                      # developer aid: phase cycle counts in k_jpeg_huff
+        extra.append("-DLSF_JPEG_PROF")
+    if os.environ.get("LSF_JPEG_LUT_BITS"):
+        extra.append("-DLSF_JPEG_LUT_BITS=" + os.environ["LSF_JPEG_LUT_BITS"])
     if os.environ.get("LSF_JT"):
         extra.append("-DLSF_JT=" + os.environ["LSF_JT"])
     if os.environ.get("LSF_GROW_PER_SM_BUILD"):                              # developer aid: occupancy experiments

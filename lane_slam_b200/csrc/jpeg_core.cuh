@@ -25,11 +25,20 @@
 namespace jd {
 
 constexpr int MAX_BPM = 6;              // blocks per MCU: 4:2:0 = 4 + 1 + 1
-constexpr int LUT_BITS = 9;
+#ifndef LSF_JPEG_LUT_BITS
+#define LSF_JPEG_LUT_BITS 10
+#endif
+constexpr int LUT_BITS = LSF_JPEG_LUT_BITS;
+static_assert(LUT_BITS == 10, "the second level assumes 10 + 6 = 16 bits");
+constexpr int LUT2_TABLES = 32;         // the standard (Annex K) tables need 13
+constexpr uint32_t LUT2_FLAG = 0x80000000u;
 
 // One Huffman table set: [0] DC table 0, [1] DC table 1, [2] AC table 0, [3] AC table 1
 struct Tabs {
-    uint16_t lut[4][1 << LUT_BITS];     // 9-bit look-ahead: (code length << 8) | symbol; 0 = longer code (or unused pattern)
+    uint32_t lut[4][1 << LUT_BITS];     // look-ahead table of lut_entry() words; 0 = no code (or one the second level has no room for);
+                                        // LUT2_FLAG | i * 64 = the codes with this prefix are longer: second-level table i
+    uint32_t lut2[LUT2_TABLES][64];     // indexed by the six bits after the first LUT_BITS (LUT_BITS + 6 = 16 = the longest code)
+    uint32_t n2;                        // second-level tables in use (all four tables of the set draw from one pool)
     int32_t maxcode[4][18];             // largest code of each length 1 .. 16 (-1: none)
     int32_t valoff[4][17];              // index of the first symbol of a length minus the smallest code of that length
     uint8_t vals[4][256];
@@ -63,6 +72,31 @@ JD_FN const uint8_t *zigzag()
 #endif
 }
 
+// What one Huffman symbol does, precomputed: symbol | code length << 8 | (code length + value bits) << 16 | zig-zag advance << 24.
+// The advance is 1 for a DC value, run + 1 for an AC value, 16 for ZRL and 64 for EOB (it is clamped to the end of the block).
+JD_FN uint32_t lut_entry(int table, uint32_t len, uint32_t sym)
+{
+    uint32_t size, adv;
+    if (table < 2) { size = sym > 15 ? 15u : sym; adv = 1; }
+    else {
+        size = sym & 15u;
+        const uint32_t run = sym >> 4;
+        adv = size ? run + 1 : (run == 15 ? 16u : 64u);
+    }
+    return sym | (len << 8) | ((len + size) << 16) | (adv << 24);
+}
+
+// the canonical search of jdhuff.c for a code of more than LUT_BITS bits at the top of v (or no code at all: 16 bits, symbol 0)
+template <typename TabsT>
+JD_FN uint32_t search_code(const TabsT &tabs, int t, uint32_t v)
+{
+    for (uint32_t l = LUT_BITS + 1; l <= 16; ++l) {
+        const int32_t code = (int32_t)(v >> (32 - l));
+        if (code <= tabs.maxcode[t][l]) return lut_entry(t, l, tabs.vals[t][(tabs.valoff[t][l] + code) & 255]);
+    }
+    return lut_entry(t, 16, 0);
+}
+
 // ---- host: header parsing and table construction ---------------------------------------------------------------------------
 inline int rd16(const uint8_t *p) { return (p[0] << 8) | p[1]; }
 
@@ -76,7 +110,16 @@ inline void build_table(const uint8_t *bits /* [1..16] */, const uint8_t *vals, 
         for (int i = 0; i < bits[l]; ++i, ++k, ++code) {
             if (l <= LUT_BITS) {
                 const int lo = code << (LUT_BITS - l), n = 1 << (LUT_BITS - l);
-                for (int j = 0; j < n; ++j) t.lut[slot][lo + j] = (uint16_t)((l << 8) | vals[k]);
+                for (int j = 0; j < n; ++j) t.lut[slot][lo + j] = lut_entry(slot, (uint32_t)l, vals[k]);
+            } else {
+                const int rem = l - LUT_BITS, prefix = code >> rem;
+                uint32_t &first = t.lut[slot][prefix];
+                if (first == 0 && t.n2 < (uint32_t)LUT2_TABLES) first = LUT2_FLAG | (t.n2++ * 64);
+                if (first & LUT2_FLAG) {
+                    uint32_t *sub = &t.lut2[0][0] + (first & 0xffffu);
+                    const int lo = (code & ((1 << rem) - 1)) << (6 - rem), n = 1 << (6 - rem);
+                    for (int j = 0; j < n; ++j) sub[lo + j] = lut_entry(slot, (uint32_t)l, vals[k]);
+                }
             }
         }
         t.maxcode[slot][l] = bits[l] ? code - 1 : -1;
@@ -182,61 +225,93 @@ inline int parse(const uint8_t *data, size_t len, Image &im, Tabs *tabs_p, uint6
 
 // ---- Huffman span decoder ----------------------------------------------------------------------------------------------------
 // words: the entropy-coded bits with the stuffed zero bytes removed, as BIG-ENDIAN 32-bit words (bit 0 of the stream is bit 31
-// of words[0]), followed by at least two zero words.
+// of words[0]), followed by at least three zero words.
 struct Span {
     uint32_t pos;       // bit position of the next symbol
     uint32_t s;         // slot * 64 + zig-zag index of the next coefficient (0 .. bpm*64 - 1)
     uint32_t adv;       // coefficient slots covered so far (64 per completed block)
 };
 
+// two spans can hold coefficients of the same block (the one that straddles their boundary): OR, atomically on the device
+JD_FN void rowmask_flush(uint32_t *rowmask, uint32_t blk, uint32_t rm)
+{
+    rm &= 0xfeu;                                         // row 0 holds the DC value: always present
+    if (!rm) return;
+#ifdef __CUDA_ARCH__
+    atomicOr(rowmask + (blk >> 2), rm << ((blk & 3) * 8));
+#else
+    rowmask[blk >> 2] |= rm << ((blk & 3) * 8);
+#endif
+}
+
+// The loop keeps a 64-bit window of the stream in registers (the next word is fetched two words ahead, so no load sits on
+// the symbol-to-symbol dependency chain) and decides with selects instead of branches (lanes of a warp decode different
+// streams; only the rare long codes and the stores diverge).
 template <typename TabsT>
 JD_FN void decode_span(const uint32_t *words, const TabsT &tabs, const int32_t *slot_dc, const int32_t *slot_ac, int bpm, Span &st,
                        uint32_t pos_limit, int16_t *coef /* or NULL */, uint32_t u_start, uint32_t max_blocks,
-                       int16_t *dcdiff = nullptr /* optional: DC differences go here (one per block) instead of coef[blk * 64] */)
+                       int16_t *dcdiff = nullptr /* optional: DC differences go here (one per block) instead of coef[blk * 64] */,
+                       uint32_t *rowmask = nullptr /* optional: one byte per block, bit r = row r (1..7) of the block holds a coefficient */,
+                       const uint8_t *zz = nullptr /* optional: the caller's copy of the zig-zag table */)
 {
     uint32_t pos = st.pos, s = st.s, adv = st.adv;
-    const uint8_t *ZZ = zigzag();
+    if (!(pos < pos_limit)) return;
+    const uint8_t *ZZ = zz ? zz : zigzag();
+    uint32_t rm = 0, rm_blk = 0;
+    uint32_t wi = pos >> 5;
+    uint32_t hi = words[wi], lo = words[wi + 1], nx = words[wi + 2];
+    uint32_t slot = s >> 6;
+    int tdc = slot_dc[slot], tac = slot_ac[slot];
     while (pos < pos_limit) {
-        const uint32_t wi = pos >> 5, sh = pos & 31;
-        const uint32_t hi = words[wi], lo = words[wi + 1];
-        const uint32_t v = sh ? ((hi << sh) | (lo >> (32 - sh))) : hi;      // the next 32 bits of the stream
-        const uint32_t slot = s >> 6, z = s & 63;
-        const int t = z == 0 ? slot_dc[slot] : slot_ac[slot];
-        uint32_t e = tabs.lut[t][v >> (32 - LUT_BITS)], len, sym;
-        if (e) { len = e >> 8; sym = e & 0xff; }
-        else {
-            len = 16; sym = 0;
-            for (uint32_t l = LUT_BITS + 1; l <= 16; ++l) {
-                const int32_t code = (int32_t)(v >> (32 - l));
-                if (code <= tabs.maxcode[t][l]) { len = l; sym = tabs.vals[t][(tabs.valoff[t][l] + code) & 255]; break; }
-            }
-        }
-        uint32_t size, run;
-        if (z == 0) { size = sym > 15 ? 15 : sym; run = 0; }
-        else { size = sym & 15; run = sym >> 4; }
-        uint32_t nz = z;            // zig-zag index the value (if any) is written at
-        bool write = false, endblk = false;
-        if (z == 0) { write = true; }
-        else if (size == 0) {
-            if (run == 15) { nz = z + 15; }        // ZRL: 16 zeros
-            else endblk = true;                     // EOB
-        } else { nz = z + run; write = true; }
-        if (nz > 63) { endblk = true; write = false; nz = 63; }   // only reachable from a wrong starting state
+        const uint32_t sh = pos & 31;
+        const uint32_t v = (uint32_t)(((((uint64_t)hi << 32) | lo) << sh) >> 32);      // the next 32 bits of the stream
+        const uint32_t z = s & 63;
+        const bool isdc = z == 0;
+        const int t = isdc ? tdc : tac;
+        uint32_t e = tabs.lut[t][v >> (32 - LUT_BITS)];
+        if (e & LUT2_FLAG) e = (&tabs.lut2[0][0])[(e & 0xffffu) + ((v >> (32 - LUT_BITS - 6)) & 63u)];
+        if (e == 0) e = search_code(tabs, t, v);        // no second-level table left for this prefix, or no such code
+        const uint32_t len = (e >> 8) & 31, sym = e & 0xff;
+        const uint32_t size = isdc ? (sym > 15 ? 15u : sym) : (sym & 15u);
+        const uint32_t run = isdc ? 0u : (sym >> 4);
+        const bool nosize = !isdc && size == 0;         // EOB or ZRL
+        const bool eob = nosize && run != 15;
+        uint32_t nz = z + run;                          // zig-zag index the value is written at (ZRL: z + 15, then + 1 below)
+        const bool over = !eob && nz > 63;              // only reachable from a wrong starting state
+        const bool endblk = eob || over;
+        const bool write = !nosize && !over;
+        nz = nz > 63 ? 63 : nz;
         if (write && coef) {
             const uint32_t bits = size ? ((v << len) >> (32 - size)) : 0;
             const int32_t val = (size && bits < (1u << (size - 1))) ? (int32_t)bits - (int32_t)(1u << size) + 1 : (int32_t)bits;
-            const uint32_t blk = (u_start + adv) >> 6;          // adv counts slots from the span's first block boundary ...
+            const uint32_t blk = (u_start + adv) >> 6;  // adv counts the slots from the span's start
             if (blk < max_blocks) {
-                if (z == 0 && dcdiff) dcdiff[blk] = (int16_t)val;
-                else coef[(size_t)blk * 64 + ZZ[nz]] = (int16_t)val;
+                if (isdc && dcdiff) dcdiff[blk] = (int16_t)val;
+                else {
+                    const uint32_t nat = ZZ[nz];
+                    coef[(size_t)blk * 64 + nat] = (int16_t)val;
+                    if (rowmask) {
+                        if (blk != rm_blk) { rowmask_flush(rowmask, rm_blk, rm); rm_blk = blk; rm = 0; }
+                        rm |= 1u << (nat >> 3);
+                    }
+                }
             }
         }
         pos += len + (write ? size : 0);
-        uint32_t znext = endblk ? 64 : nz + 1;
+        const uint32_t znext = endblk ? 64 : nz + 1;
         adv += znext - z;
-        if (znext >= 64) s = ((slot + 1 == (uint32_t)bpm) ? 0 : slot + 1) << 6;
-        else s = (slot << 6) | znext;
+        if (znext >= 64) {
+            slot = (slot + 1 == (uint32_t)bpm) ? 0 : slot + 1;
+            tdc = slot_dc[slot]; tac = slot_ac[slot];
+            s = slot << 6;
+        } else s = (slot << 6) | znext;
+        const uint32_t nwi = pos >> 5;
+        if (nwi != wi) {                                // at most one word further (a symbol is at most 27 bits)
+            wi = nwi; hi = lo; lo = nx;
+            nx = words[wi + 2];
+        }
     }
+    if (rowmask) rowmask_flush(rowmask, rm_blk, rm);
     st.pos = pos; st.s = s; st.adv = adv;
 }
 
@@ -278,6 +353,35 @@ JD_FN void idct_block(const int16_t *coef, const uint16_t *q, uint8_t *out, int 
                 coef[40 + c] * q[40 + c], coef[48 + c] * q[48 + c], coef[56 + c] * q[56 + c], o);
 #pragma unroll
         for (int r = 0; r < 8; ++r) ws[8 * r + c] = descale(o[r], 11);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        int o[8];
+        idct_1d(ws[8 * r], ws[8 * r + 1], ws[8 * r + 2], ws[8 * r + 3], ws[8 * r + 4], ws[8 * r + 5], ws[8 * r + 6], ws[8 * r + 7], o);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) out[r * stride + c] = range_limit(descale(o[c], 18));
+    }
+}
+
+// the same with the rows that hold no coefficient left out (rows: bit r = row r may be non-zero; row 0 always is): exactly what
+// idct_block computes when those rows are zero -- a column whose only entry is row 0 transforms to d0 << 2 in every row
+JD_FN void idct_block_rows(const int16_t *coef, const uint16_t *q, uint32_t rows, uint8_t *out, int stride)
+{
+    int ws[64];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        int d[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) d[r] = (r == 0 || ((rows >> r) & 1)) ? coef[8 * r + c] * q[8 * r + c] : 0;
+        if ((rows & 0xfeu) == 0) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) ws[8 * r + c] = d[0] << 2;
+        } else {
+            int o[8];
+            idct_1d(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], o);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) ws[8 * r + c] = descale(o[r], 11);
+        }
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {

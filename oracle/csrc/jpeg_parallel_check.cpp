@@ -14,7 +14,7 @@ int jpc_decode(const uint8_t *data, size_t len, uint8_t *bgr, int sub_bytes, int
     int rc = jd::parse(data, len, im, &tabs);
     if (rc) return rc;
     if (im.restart) return -2;
-    // stuffing removal -> big-endian words (+ 2 zero words)
+    // stuffing removal -> big-endian words (+ 3 zero words)
     std::vector<uint8_t> clean;
     clean.reserve(im.ent_len);
     const uint8_t *e = data + im.ent_off;
@@ -22,7 +22,7 @@ int jpc_decode(const uint8_t *data, size_t len, uint8_t *bgr, int sub_bytes, int
         if (e[i] == 0x00 && i > 0 && e[i - 1] == 0xFF) continue;
         clean.push_back(e[i]);
     }
-    const uint32_t nbytes = (uint32_t)clean.size(), nwords = (nbytes + 3) / 4 + 2;
+    const uint32_t nbytes = (uint32_t)clean.size(), nwords = (nbytes + 3) / 4 + 3;
     std::vector<uint32_t> words(nwords, 0);
     for (uint32_t i = 0; i < nbytes; ++i) words[i >> 2] |= (uint32_t)clean[i] << (24 - 8 * (i & 3));
     const uint32_t total_bits = nbytes * 8;
@@ -64,11 +64,12 @@ int jpc_decode(const uint8_t *data, size_t len, uint8_t *bgr, int sub_bytes, int
     for (int i = 1; i < nsub; ++i) ustart[i] = ustart[i - 1] + E[i - 1].adv;
     // phase D: write
     std::vector<int16_t> coef((size_t)nblocks * 64, 0);
+    std::vector<uint32_t> rowmask(nblocks / 4 + 1, 0);
     for (int i = 0; i < nsub; ++i) {
         jd::Span st;
         if (i == 0) { st.pos = 0; st.s = 0; } else { st.pos = E[i - 1].pos; st.s = E[i - 1].s; }
         st.adv = 0;
-        jd::decode_span(words.data(), tabs, im.slot_dc, im.slot_ac, im.bpm, st, limit(i), coef.data(), ustart[i], nblocks);
+        jd::decode_span(words.data(), tabs, im.slot_dc, im.slot_ac, im.bpm, st, limit(i), coef.data(), ustart[i], nblocks, nullptr, rowmask.data());
     }
     // DC prediction per component, in decode order
     int pred[3] = {0, 0, 0};
@@ -83,7 +84,12 @@ int jpc_decode(const uint8_t *data, size_t len, uint8_t *bgr, int sub_bytes, int
     for (uint32_t b = 0; b < nblocks; ++b) {
         const int slot = b % im.bpm, mcu = b / im.bpm, c = im.slot_comp[slot];
         const int bx = (mcu % im.mcux) * im.hs[c] + im.slot_bx[slot], by = (mcu / im.mcux) * im.vs[c] + im.slot_by[slot];
-        jd::idct_block(&coef[(size_t)b * 64], im.q[c], &plane[c][((size_t)by * 8) * (im.bw[c] * 8) + bx * 8], im.bw[c] * 8);
+        // rows the decoder did not flag are not read (the GPU kernel leaves them out the same way): poison them to prove it
+        const uint32_t rows = (rowmask[b >> 2] >> ((b & 3) * 8)) & 0xff;
+        int16_t blkc[64];
+        for (int k = 0; k < 64; ++k) blkc[k] = (k < 8 || ((rows >> (k >> 3)) & 1)) ? coef[(size_t)b * 64 + k] : (int16_t)0x5a5a;
+        for (int k = 8; k < 64; ++k) if (!((rows >> (k >> 3)) & 1) && coef[(size_t)b * 64 + k] != 0) return -6;
+        jd::idct_block_rows(blkc, im.q[c], rows, &plane[c][((size_t)by * 8) * (im.bw[c] * 8) + bx * 8], im.bw[c] * 8);
     }
     // upsample + colour
     for (int y = 0; y < im.H; ++y)
