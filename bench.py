@@ -132,6 +132,7 @@ def make_frames(n, base_seed, start=0, h=H, w=W, dense=False):
     return synth.sequence(n, base_seed=base_seed, H=h, W=w, dense=dense, start=start)
 
 
+EXTRAS_DEADLINE_S = 300          # extra configurations (c5 runs collectives): give up after this many seconds at N > 1
 JPEG_QUALITY = 90
 
 
@@ -325,18 +326,26 @@ def run_gpu(args):
     kept_seen = [0]
     last = [None] * T
 
-    def step(c, kind):
+    def run_batch(c, kind):
         f = fes[c]
         f.reset_sequence()
         if kind == "jpeg":
             b = f.process_jpeg(blobs[c], off, stages=stages, k=K_NN)
         else:
             b = f.process(dev if kind == "dev" else pinned.numpy(), stages=stages, k=K_NN)
+        last[c] = b
+        return b
+
+    def exchange(c):
         if world > 1:
+            f = fes[c]
             if inflight[c]:                                   # the exchange of this context's previous step ran under this step's kernels
                 _, ntot, _ = f.exchange_wait(); inflight[c] -= 1; kept_seen[0] = ntot
             f.allgather_start(frame_base=rank * n); inflight[c] += 1
-        last[c] = b
+
+    def step(c, kind):
+        b = run_batch(c, kind)
+        exchange(c)
         return b
 
     def drain(c):
@@ -372,8 +381,13 @@ def run_gpu(args):
                 for i in range(c, steps, ncontexts):
                     if stream_ahead and i + 1 < steps:
                         fes[c].prefetch(pinned.numpy())
-                    b = step(c, kind)
-                    if c == 0:
+                    try:
+                        b = run_batch(c, kind)
+                    except Exception as e:      # the exchange below still runs (previous records): the ranks' collectives stay matched
+                        errors.append(repr(e))
+                        b = None
+                    exchange(c)
+                    if c == 0 and b is not None:
                         for name, ms in fes[0].timings():
                             stage_ms[name] = stage_ms.get(name, 0.0) + ms
                         S = b.n_segments
@@ -396,11 +410,24 @@ def run_gpu(args):
         start.wait()
         for t in ths:
             t.join()
-        if errors:
-            raise RuntimeError("bench step failed: %s" % errors)
+        failed = 1 if errors else 0
+        if world > 1:                                        # every rank takes the same branch below
+            ft = torch.tensor([failed], dtype=torch.int32, device="cuda")
+            dist.all_reduce(ft, op=dist.ReduceOp.MAX)
+            failed = int(ft.item())
         barrier()
+        if failed:
+            raise RuntimeError("bench step failed (%s input, %d context(s)): %s" % (kind, ncontexts, errors or "on another rank"))
         dt = max(e0.elapsed_time(e) for e in e1) * 1e-3
         return dt, stage_ms, d2h[0], last[0]
+
+    def timed_secondary(kind, steps, **kw):
+        """A measurement that explains the headline but is not the headline: a failure is reported as null, not fatal."""
+        try:
+            return timed(kind, steps, **kw)
+        except RuntimeError as e:
+            print("[bench] %s" % e, file=sys.stderr, flush=True)
+            return float("nan"), {}, 0, None
 
     log("contexts ready")
     # warm-up (>= 3 per context and input kind)
@@ -423,9 +450,9 @@ def run_gpu(args):
     jpeg_same = bool(bj.n_segments == b.n_segments and np.array_equal(bj.lines_px, b.lines_px) and np.array_equal(bj.desc, b.desc))
     fe.set_chunk_frames(0)                                                         # one batch at a time: chunk pipeline inside the batch
     step(0, "dev"); step(0, "jpeg"); drain(0)
-    dt_dev1, _, _, _ = timed("dev", args.steps, ncontexts=1)
-    dt_jpeg1, jpeg_stage_ms, _, _ = timed("jpeg", args.steps, ncontexts=1)
-    dt_raw, _, _, _ = timed("raw", args.steps, ncontexts=1, stream_ahead=True)     # round-1 e2e: raw BGR host frames, staged one step ahead
+    dt_dev1, _, _, _ = timed_secondary("dev", args.steps, ncontexts=1)
+    dt_jpeg1, jpeg_stage_ms, _, _ = timed_secondary("jpeg", args.steps, ncontexts=1)
+    dt_raw, _, _, _ = timed_secondary("raw", args.steps, ncontexts=1, stream_ahead=True)   # round-1 e2e: raw BGR host frames, staged one step ahead
     # per-kernel times for the roofline: same steps on ONE stream (chunk pipeline off) so that the library's
     # CUDA events bracket each kernel; not part of `value` / `e2e`
     fe.set_chunk_frames(-1)
@@ -451,8 +478,120 @@ def run_gpu(args):
     extra = {}
     for f in fes[1:]:
         f.close()
+    if world > 1:
+        t = torch.tensor([dt_dev, dt_e2e, dt_dev1, dt_jpeg1, dt_raw], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_dev, dt_e2e, dt_dev1, dt_jpeg1, dt_raw = [float(x) for x in t]
+    finish_lock = threading.Lock()
+    finished = [False]
+
+    def finish():
+        """Rank 0: build and print the one JSON line (once)."""
+        with finish_lock:
+            if finished[0]:
+                return
+            finished[0] = True
+            finish_locked()
+
+    def finish_locked():
+        total_frames = n * world * args.steps
+        value = total_frames / dt_dev
+        e2e = total_frames / dt_e2e
+
+        def rate(dt):
+            return total_frames / dt if np.isfinite(dt) and dt > 0 else None
+
+        def ms_step(dt):
+            return 1e3 * dt / args.steps if np.isfinite(dt) and dt > 0 else None
+        peak, peak_src = peaks()
+        kernels = []
+        tot_ms = sum(v for k, v in stage_ms.items() if k not in ("h2d", "d2h"))
+        for name, ms in sorted(stage_ms.items(), key=lambda kv: -kv[1]):
+            if name in ("h2d", "d2h"):
+                continue
+            per = ms / args.steps
+            ent = {"kernel": name, "ms_per_step": per, "share": ms / tot_ms}
+            if name in ALGO_BYTES:
+                gbs = ALGO_BYTES[name] * n / (per * 1e-3) / 1e9
+                ent.update(bound="hbm", algorithmic_bytes_per_frame=ALGO_BYTES[name], achieved_gbs=gbs, frac=gbs / peak,
+                           dram_traffic_bytes_per_launch=TRAFFIC_BYTES[name] * n)
+            else:
+                ent.update(bound="latency")
+            kernels.append(ent)
+        dense = [k for k in kernels if k["bound"] == "hbm"]
+        dom = max(dense, key=lambda k: k["ms_per_step"])
+        roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": dom["frac"], "traffic": dom["dram_traffic_bytes_per_launch"],
+                    "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_frame"] * n, "peak_source": peak_src,
+                    "traffic_source": TRAFFIC_SOURCE % n,
+                    "note": "dominant HBM-bound kernel; the LSD search (lsd_core) is latency-bound, see 'kernels'"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": 1e3 * dt_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/f64", "data": "synthetic",
+            "config": workload_config(n),
+            "pipeline": {"contexts_in_flight": T,
+                         "how": "%d contexts per GPU, one host thread each, consecutive steps dealt round robin (batches overlap on the GPU); "
+                                "with several contexts every batch runs on one stream (the chunk pipeline is for one batch at a time)" % T,
+                         "one_batch_at_a_time": {"value": rate(dt_dev1), "ms_per_step": ms_step(dt_dev1),
+                                                 "e2e_jpeg_value": rate(dt_jpeg1), "e2e_jpeg_ms_per_step": ms_step(dt_jpeg1)},
+                         "segments_per_step": seg_per_step, "kept_per_step": kept_per_step,
+                         "exchange": None if world == 1 else "lsf_allgather_segments: one ncclAllGather of fixed-capacity slots on the ctx's exchange "
+                                                            "stream, started after step i and finished under step i+1 (last one inside the timed region); "
+                                                            "%d records gathered per step" % kept_seen[0]},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(off[-1]) + n * (16 + 384) + 8192, "d2h_bytes_per_step": int(d2h_bytes),
+                    "ms_per_step": 1e3 * dt_e2e / args.steps,
+                    "how": "the frames as JPEG files in pinned host memory through FrontEnd.process_jpeg (lsf_front_end_batch_jpeg): every step "
+                           "parses the headers, copies the compressed bytes to the device, decodes them on the GPU (bit-identical to "
+                           "cv2.imdecode), runs the whole front end and copies the segment lists back, all inside the timed region",
+                    "jpeg_bytes_per_frame": float(off[-1]) / n, "jpeg_quality": JPEG_QUALITY,
+                    "same_result_as_value_arm": jpeg_same,
+                    "decode_stage_ms_per_step": {k: v / args.steps for k, v in jpeg_stage_ms.items() if k.startswith("jpeg")},
+                    "raw_bgr": {"value": rate(dt_raw), "ms_per_step": ms_step(dt_raw), "h2d_bytes_per_step": int(n * H * W * 3),
+                                "how": "round-1 definition: decoded BGR frames in pinned host memory, H2D staged one step ahead (PCIe-bound)"}},
+            "gpu_launches": int(launches),
+            "latency": dict(lat, batch1000_ms_per_frame_amortised=1e3 * dt_dev / args.steps / n,
+                            batch1000_step_ms=1e3 * dt_dev / args.steps) if lat else None,
+            "roofline": roofline, "kernels": kernels, "clocks": clocks, "parity": parity, "extra_configs": extra,
+        }
+        if world == 1 and not args.no_cpu:
+            # the CPU leg runs in a fresh interpreter (no CUDA state), bounded in time
+            try:
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                                     capture_output=True, text=True, timeout=600)
+                ref = json.loads(out.stdout.strip().splitlines()[-1])
+                line["cpu_baseline"] = ref["cpu_baseline"]
+            except Exception as e:  # the GPU numbers stand on their own
+                line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                        "sample": "failed: %r" % (e,)}
+        emit(line)
+
+    if world > 1 and args.extras:
+        # The headline is measured; the extra configurations below still run collectives.  Should one of them never return
+        # (a rank that failed leaves the others waiting), the line is printed without it and every rank leaves.
+        def watchdog():
+            time.sleep(EXTRAS_DEADLINE_S)
+            if finished[0]:
+                return
+            if rank == 0:
+                extra.setdefault("c5", {"error": "not finished after %d s, abandoned" % EXTRAS_DEADLINE_S})
+                try:
+                    finish()
+                finally:
+                    os._exit(0)
+            time.sleep(20)
+            os._exit(0)
+        threading.Thread(target=watchdog, daemon=True).start()
     if "c5" in args.extras:
-        extra["c5"] = bench_c5(torch, dist, L, fe, dev, n, rank, world, local, args, log)
+        try:
+            extra["c5"] = bench_c5(torch, dist, L, fe, dev, n, rank, world, local, args, log)
+        except Exception as e:                    # the headline stands on its own
+            print("[bench] c5 failed: %r" % (e,), file=sys.stderr, flush=True)
+            extra["c5"] = {"error": repr(e)}
+            if world > 1:                         # the ranks are out of step: no more collectives
+                if rank == 0:
+                    finish()
+                os._exit(0)
     fe.close()
     del dev
     torch.cuda.empty_cache()
@@ -461,79 +600,12 @@ def run_gpu(args):
             extra["c4"] = bench_c4(torch, L, local, log)
         if "c3" in args.extras:
             extra["c3"] = bench_c3(torch, L, local, args, log)
-    if world > 1:
-        t = torch.tensor([dt_dev, dt_e2e, dt_dev1, dt_jpeg1, dt_raw], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt_dev, dt_e2e, dt_dev1, dt_jpeg1, dt_raw = [float(x) for x in t]
     if rank != 0:
+        finished[0] = True
         if world > 1:
             dist.destroy_process_group()
         return
-    total_frames = n * world * args.steps
-    value = total_frames / dt_dev
-    e2e = total_frames / dt_e2e
-    peak, peak_src = peaks()
-    kernels = []
-    tot_ms = sum(v for k, v in stage_ms.items() if k not in ("h2d", "d2h"))
-    for name, ms in sorted(stage_ms.items(), key=lambda kv: -kv[1]):
-        if name in ("h2d", "d2h"):
-            continue
-        per = ms / args.steps
-        ent = {"kernel": name, "ms_per_step": per, "share": ms / tot_ms}
-        if name in ALGO_BYTES:
-            gbs = ALGO_BYTES[name] * n / (per * 1e-3) / 1e9
-            ent.update(bound="hbm", algorithmic_bytes_per_frame=ALGO_BYTES[name], achieved_gbs=gbs, frac=gbs / peak,
-                       dram_traffic_bytes_per_launch=TRAFFIC_BYTES[name] * n)
-        else:
-            ent.update(bound="latency")
-        kernels.append(ent)
-    dense = [k for k in kernels if k["bound"] == "hbm"]
-    dom = max(dense, key=lambda k: k["ms_per_step"])
-    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": dom["frac"], "traffic": dom["dram_traffic_bytes_per_launch"],
-                "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_frame"] * n, "peak_source": peak_src,
-                "traffic_source": TRAFFIC_SOURCE % n,
-                "note": "dominant HBM-bound kernel; the LSD search (lsd_core) is latency-bound, see 'kernels'"}
-    line = {
-        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": 1e3 * dt_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8/f64", "data": "synthetic",
-        "config": workload_config(n),
-        "pipeline": {"contexts_in_flight": T,
-                     "how": "%d contexts per GPU, one host thread each, consecutive steps dealt round robin (batches overlap on the GPU); "
-                            "with several contexts every batch runs on one stream (the chunk pipeline is for one batch at a time)" % T,
-                     "one_batch_at_a_time": {"value": total_frames / dt_dev1, "ms_per_step": 1e3 * dt_dev1 / args.steps,
-                                             "e2e_jpeg_value": total_frames / dt_jpeg1, "e2e_jpeg_ms_per_step": 1e3 * dt_jpeg1 / args.steps},
-                     "segments_per_step": seg_per_step, "kept_per_step": kept_per_step,
-                     "exchange": None if world == 1 else "lsf_allgather_segments: one ncclAllGather of fixed-capacity slots on the ctx's exchange "
-                                                        "stream, started after step i and finished under step i+1 (last one inside the timed region); "
-                                                        "%d records gathered per step" % kept_seen[0]},
-        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(off[-1]) + n * (16 + 384) + 8192, "d2h_bytes_per_step": int(d2h_bytes),
-                "ms_per_step": 1e3 * dt_e2e / args.steps,
-                "how": "the frames as JPEG files in pinned host memory through FrontEnd.process_jpeg (lsf_front_end_batch_jpeg): every step "
-                       "parses the headers, copies the compressed bytes to the device, decodes them on the GPU (bit-identical to "
-                       "cv2.imdecode), runs the whole front end and copies the segment lists back, all inside the timed region",
-                "jpeg_bytes_per_frame": float(off[-1]) / n, "jpeg_quality": JPEG_QUALITY,
-                "same_result_as_value_arm": jpeg_same,
-                "decode_stage_ms_per_step": {k: v / args.steps for k, v in jpeg_stage_ms.items() if k.startswith("jpeg")},
-                "raw_bgr": {"value": total_frames / dt_raw, "ms_per_step": 1e3 * dt_raw / args.steps, "h2d_bytes_per_step": int(n * H * W * 3),
-                            "how": "round-1 definition: decoded BGR frames in pinned host memory, H2D staged one step ahead (PCIe-bound)"}},
-        "gpu_launches": int(launches),
-        "latency": dict(lat, batch1000_ms_per_frame_amortised=1e3 * dt_dev / args.steps / n,
-                        batch1000_step_ms=1e3 * dt_dev / args.steps) if lat else None,
-        "roofline": roofline, "kernels": kernels, "clocks": clocks, "parity": parity, "extra_configs": extra,
-    }
-    if world == 1 and not args.no_cpu:
-        # the CPU leg runs in a fresh interpreter (no CUDA state), bounded in time
-        try:
-            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                                 capture_output=True, text=True, timeout=600)
-            ref = json.loads(out.stdout.strip().splitlines()[-1])
-            line["cpu_baseline"] = ref["cpu_baseline"]
-        except Exception as e:  # the GPU numbers stand on their own
-            line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": "failed: %r" % (e,)}
-    emit(line)
+    finish()
     if world > 1:
         dist.destroy_process_group()
 

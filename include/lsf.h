@@ -79,7 +79,8 @@ typedef struct lsf_config {
     int32_t max_batch;           /* frames per call the scratch is sized for */
     int32_t max_src_h, max_src_w;/* largest input frame */
     int32_t max_segments_per_color; /* per frame and colour */
-    int32_t max_pixels_per_color;   /* LSD support pixels per frame and colour */
+    int32_t max_pixels_per_color;   /* LSD support pixels per frame and colour; 0 = sized by the library, which then grows it and reruns
+                                       the batch when a frame needs more (a value set here is a hard limit: LSF_E_CAPACITY) */
     int32_t device;              /* CUDA device ordinal */
     int32_t chunk_frames;        /* frames per pipeline chunk: a batch is cut into chunks whose host->device copy and
                                     kernels overlap on several streams.  0 = automatic (n/8 for host frames, n/2 for

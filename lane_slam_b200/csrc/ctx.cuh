@@ -25,6 +25,7 @@ struct lsf_ctx {
     CamParams cam;
     int max_batch, max_src_h, max_src_w;
     int h, w, wp, sh, sw, swp, pixcap, segcap;
+    bool pixcap_auto;                    // max_pixels_per_color was left to the library: it grows on demand
     bool have_batch;
     const u8 *last_src;   // device pointer of the last batch's frames
     // map of descriptors

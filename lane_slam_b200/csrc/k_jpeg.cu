@@ -227,8 +227,9 @@ __global__ void __launch_bounds__(JT) k_jpeg_huff(jd::Image g, const u8 *__restr
         const u32 bal = __ballot_sync(0xffffffffu, dirty);
         if (lane == 0) s_scan[warp] = __popc(bal);
         E[cur ^ 1][t] = E[cur][t];
-        s_chg[t] = 0;
         __syncthreads();
+        s_chg[t] = 0;                                  // only now: before the barrier a slower warp may still be reading the previous
+                                                       // round's flag of its left neighbour (the `dirty` line at the end of the loop)
         int off = 0, nd = 0;
         for (int k = 0; k < NW; ++k) { const int w = s_scan[k]; if (k < warp) off += w; nd += w; }
         if (dirty) s_list[off + __popc(bal & ((1u << lane) - 1))] = (u16)t;

@@ -105,6 +105,7 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     ctx->pixcap = cfg->max_pixels_per_color > 0 ? cfg->max_pixels_per_color
                                                 : (int)(ctx->max_batch <= 128 ? Np : std::max<size_t>(4096, Np / 8));
     if ((size_t)ctx->pixcap > Np) ctx->pixcap = (int)Np;
+    ctx->pixcap_auto = cfg->max_pixels_per_color <= 0;
     ctx->segcap = cfg->max_segments_per_color > 0 ? cfg->max_segments_per_color
                                                   : (int)std::max<size_t>(512, (size_t)ctx->h * ctx->w / 256);
     for (int i = 0; i < 4; ++i)
@@ -327,6 +328,31 @@ extern "C" void *lsf_stream(lsf_ctx *ctx) { return ctx ? (void *)ctx->st : nullp
 extern "C" const char *lsf_version(void) { return "lsf 0.1 (sm_100a)"; }
 
 // host -> device copy of `rows` rows of `row_bytes` bytes: one linear copy when the host rows are contiguous
+// every buffer whose size follows max_pixels_per_color, reallocated for a larger capacity (the batch is over: nothing reads them)
+static int regrow_pixcap(lsf_ctx *ctx, int need)
+{
+    Buffers &b = ctx->b;
+    const size_t n = ctx->max_batch, Np = (size_t)ctx->sh * ctx->sw;
+    const size_t cap = std::min(Np, (((size_t)need + (size_t)need / 4 + 1023) / 1024) * 1024);
+    CK(cudaDeviceSynchronize());
+    for (void *p : {(void *)b.pix, (void *)b.pxy, (void *)b.fat, (void *)b.scs, (void *)b.usedbits, (void *)b.order, (void *)b.label, (void *)b.csize,
+                    (void *)b.coff, (void *)b.corder, (void *)b.cpos, (void *)b.reg})
+        if (p) cudaFree(p);
+    b.pix = nullptr; b.pxy = nullptr; b.fat = nullptr; b.scs = nullptr; b.usedbits = nullptr; b.order = nullptr; b.label = nullptr; b.csize = nullptr;
+    b.coff = nullptr; b.corder = nullptr; b.cpos = nullptr; b.reg = nullptr;
+    ctx->pixcap = (int)cap;
+    CK(dalloc(&b.pix, n * 3 * cap));
+    CK(dalloc(&b.pxy, n * 3 * cap));
+    CK(dalloc(&b.fat, n * 3 * cap * LSD_FAT_WORDS));
+    CK(dalloc(&b.scs, n * 3 * cap));
+    CK(dalloc(&b.usedbits, n * 3 * ((cap + 31) / 32)));
+    CK(dalloc(&b.order, n * 3 * cap));
+    CK(dalloc(&b.label, n * 3 * cap)); CK(dalloc(&b.csize, n * 3 * cap)); CK(dalloc(&b.coff, n * 3 * cap));
+    CK(dalloc(&b.corder, n * 3 * cap)); CK(dalloc(&b.cpos, n * 3 * cap));
+    CK(dalloc(&b.reg, n * 3 * cap * 2));
+    return LSF_OK;
+}
+
 static cudaError_t h2d_rows(void *dst, const void *src, size_t src_pitch, size_t row_bytes, size_t rows, cudaStream_t st)
 {
     if (src_pitch == row_bytes) return cudaMemcpyAsync(dst, src, row_bytes * rows, cudaMemcpyHostToDevice, st);
@@ -576,6 +602,13 @@ extern "C" int lsf_front_end_batch(lsf_ctx *ctx, const uint8_t *bgr, int n, int 
             ctx->grow_bits_hint = std::min(ctx->pixcap, std::max(ctx->grow_bits_hint, ((flags[5] + flags[5] / 2 + 1023) / 1024) * 1024));
             return lsf_front_end_batch(ctx, bgr, n, src_h, src_w, pitch, mem_kind, stages, k, out);
         }
+    }
+    if (flags[0] && ctx->pixcap_auto && (size_t)ctx->pixcap < (size_t)ctx->sh * ctx->sw) {
+        // the default capacity (an eighth of the scaled image for large batches) was a guess: size it from this batch's count
+        // (+25 %) and run the batch again.  A capacity the caller set is a contract and stays an error.
+        int rc = regrow_pixcap(ctx, flags[0]);
+        if (rc) return rc;
+        return lsf_front_end_batch(ctx, bgr, n, src_h, src_w, pitch, mem_kind, stages, k, out);
     }
     if (flags[0]) return fail(ctx, LSF_E_CAPACITY, "LSD support pixels of one colour image = " + std::to_string(flags[0]) +
                                                        " exceed max_pixels_per_color = " + std::to_string(ctx->pixcap));
