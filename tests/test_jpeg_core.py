@@ -22,11 +22,12 @@ def sim(tmp_path_factory):
     subprocess.check_call(["g++", "-std=c++14", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "oracle", "csrc", "jpeg_parallel_check.cpp")])
     lib = C.CDLL(so)
 
-    def decode(data, shape, sub_bytes):
+    def decode(data, shape, sub_bytes, gpu_loop=False):
         b = np.ascontiguousarray(data, np.uint8)
         out = np.zeros(shape, np.uint8)
         r, n = C.c_int(), C.c_int()
-        rc = lib.jpc_decode(b.ctypes.data_as(C.c_void_p), C.c_size_t(len(b)), out.ctypes.data_as(C.c_void_p), int(sub_bytes), C.byref(r), C.byref(n))
+        fn = lib.jpc_decode_gpu_loop if gpu_loop else lib.jpc_decode
+        rc = fn(b.ctypes.data_as(C.c_void_p), C.c_size_t(len(b)), out.ctypes.data_as(C.c_void_p), int(sub_bytes), C.byref(r), C.byref(n))
         return rc, out, r.value, n.value
     return decode
 
@@ -58,3 +59,32 @@ def test_parallel_decode_samplings_sizes_qualities(sim):
     assert sim(enc, (480, 640, 3), 64)[0] == -2                 # outside the scope: reported, not mis-decoded
     ok, enc = cv2.imencode('.jpg', synth.frame(1), [cv2.IMWRITE_JPEG_RST_INTERVAL, 4])
     assert sim(enc, (480, 640, 3), 64)[0] == -2
+
+
+def test_the_kernels_own_symbol_loop_equals_cv2(sim):
+    """k_jpeg.cu decodes with a loop of its own (64-bit bit buffer, two-level table word per symbol, packed table selector); its
+    host restatement (gpu_scan_span in jpeg_parallel_check.cpp), run with the kernel's geometry -- 512 subsequences per image,
+    20 zero bytes and then garbage behind the stream -- must converge and reproduce cv2.imdecode: real frames, every sampling,
+    optimised Huffman tables (long codes, second-level tables), very low and very high quality, noise, grayscale."""
+    for i in range(realset.count()):
+        img = realset.image(i)
+        rc, out, rounds, nsub = sim(realset.jpeg(i), img.shape, 0, gpu_loop=True)
+        assert rc == 0 and np.array_equal(out, img), i
+        assert nsub <= 512 and rounds < 64
+    rng = np.random.default_rng(0)
+    images = [synth.frame(2), synth.frame(7, 123, 161), rng.integers(0, 256, (96, 128, 3), dtype=np.uint8)]
+    P = cv2
+    for q in (5, 60, 100):
+        for extra in ([], [P.IMWRITE_JPEG_OPTIMIZE, 1], [P.IMWRITE_JPEG_SAMPLING_FACTOR, P.IMWRITE_JPEG_SAMPLING_FACTOR_444],
+                      [P.IMWRITE_JPEG_SAMPLING_FACTOR, P.IMWRITE_JPEG_SAMPLING_FACTOR_422, P.IMWRITE_JPEG_OPTIMIZE, 1],
+                      [P.IMWRITE_JPEG_SAMPLING_FACTOR, P.IMWRITE_JPEG_SAMPLING_FACTOR_440]):
+            for im in images:
+                ok, enc = cv2.imencode('.jpg', im, [P.IMWRITE_JPEG_QUALITY, q] + extra)
+                ref = cv2.imdecode(enc, cv2.IMREAD_COLOR)
+                for sub in (0, 16):
+                    rc, out, _, _ = sim(enc, ref.shape, sub, gpu_loop=True)
+                    assert rc == 0 and np.array_equal(out, ref), (q, extra, im.shape, sub)
+    ok, enc = cv2.imencode('.jpg', cv2.cvtColor(synth.frame(1), cv2.COLOR_BGR2GRAY), [P.IMWRITE_JPEG_QUALITY, 100, P.IMWRITE_JPEG_OPTIMIZE, 1])
+    ref = cv2.imdecode(enc, cv2.IMREAD_COLOR)
+    rc, out, _, _ = sim(enc, ref.shape, 0, gpu_loop=True)
+    assert rc == 0 and np.array_equal(out, ref)
