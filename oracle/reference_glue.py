@@ -119,6 +119,39 @@ def normals_and_ordering(bw, lines):
     return centers, normals
 
 
+def hough_lines_cv(edge_img, threshold, min_line_length, max_line_gap):
+    """line_detector1.py:63-69 (_HoughLine): int32 [S,4], or the plain list [] when nothing is found."""
+    lines = cv2.HoughLinesP(edge_img, 1, np.pi / 180, threshold, np.empty(1), min_line_length, max_line_gap)
+    return [] if lines is None else np.array(lines[:, 0])
+
+
+class LineDetectorHSV:
+    """Same plugin contract as src/line_detector/include/line_detector/line_detector1.py:11-137 (the detector eight of the ten
+    shipped YAML files select): setImage and the colour filter are the LSD detector's, the lines come from cv2.HoughLinesP and are
+    int32, so _findNormal's arithmetic (the same source lines as in line_detector_lsd.py) runs in float64 here."""
+
+    def __init__(self, configuration):
+        self.cfg = check_configuration(configuration)
+        self.hough = tuple(int(configuration[k]) for k in ('hough_threshold', 'hough_min_line_length', 'hough_max_line_gap'))
+        self.bgr = self.hsv = self.edges = np.empty(0)
+
+    def setImage(self, bgr):  # :127-130
+        self.bgr = np.copy(bgr)
+        self.hsv = cv2.cvtColor(bgr, cv2.COLOR_BGR2HSV)
+        lo, hi = self.cfg['canny_thresholds']
+        self.edges = cv2.Canny(self.bgr, lo, hi, apertureSize=3)
+
+    def detectLines(self, color):  # :121-125
+        bw = color_mask_cv(self.hsv, self.cfg, color)
+        edge_color = cv2.bitwise_and(bw, self.edges)
+        lines = hough_lines_cv(edge_color, *self.hough)
+        centers, normals = normals_and_ordering(bw, lines)
+        return Detections(lines=lines, normals=normals, area=bw, centers=centers)
+
+    def getImage(self):
+        return self.bgr
+
+
 class LineDetectorLSD:
     """Same plugin contract as src/line_detector/include/line_detector/line_detector_lsd.py:11-142
     (setImage / detectLines / getImage), built from the cv2 calls above."""
