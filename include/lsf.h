@@ -328,6 +328,19 @@ LSF_API void *lsf_stream(lsf_ctx *ctx);
 
 LSF_API const char *lsf_version(void);
 
+/* ---- alternative detector: LineDetectorHSV (src/line_detector/include/line_detector/line_detector1.py:11-137; the class eight of
+ * the ten shipped line_detector_node YAML files select).  setImage and the colour filter are the ones of LineDetectorLSD and are
+ * on the device after lsf_front_end_batch / lsf_front_end_batch_jpeg (LSF_STAGE_DETECT); this call replaces detectLines for the
+ * three colours of every frame of that LAST batch: cv2.HoughLinesP(edge_color, 1, pi/180, hough_threshold, minLineLength =
+ * hough_min_line_length, maxLineGap = hough_max_line_gap) (:63-69, bit-identical line lists, same order), _findNormal and
+ * _correctPixelOrdering (:71-119, float64), toSegmentMsg's normalisation (line_detector_node.py:251-265) and -- project_ground != 0
+ * -- ground projection + line sanity as in LSF_STAGE_GROUND.  out: color, lines_px (the int32 endpoints, exactly representable),
+ * normals, centers, pixels_normalized, normal_f32, [ground, keep], counts [n][3], frame_offset [n + 1]; desc / match_* are not
+ * written (the reference's LineDetectorHSV has no descriptors).  Errors: LSF_E_ARG without a previous batch, LSF_E_CONFIG for
+ * parameters HoughLinesP would turn into degenerate lines (min length < 1), LSF_E_CAPACITY. */
+LSF_API int lsf_hough_batch(lsf_ctx *ctx, int hough_threshold, int hough_min_line_length, int hough_max_line_gap, int project_ground,
+                            lsf_segments *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,7 @@ from ._lib import (LsfError, STAGE_DESCRIBE, STAGE_DETECT, STAGE_GROUND, STAGE_M
                    TIES_REFERENCE, TIES_INDEX, MATCH_RADIUS, LIB_PATH, exported_symbols)
 from .frontend import (FrontEnd, SegmentBatch, DEFAULT_DETECTOR_CONFIGURATION, DETECTOR_PARAM_NAMES, COLORS,
                        WHITE, YELLOW, RED, scaled_calibration, check_detector_configuration)
-from .line_detector import LineDetectorB200, Detections, LineDetectorInterface
+from .line_detector import LineDetectorB200, LineDetectorHSVB200, Detections, LineDetectorInterface
 from .lane_filter import LaneFilterB200
 from . import wire, odometry, replay
 from .messages import Segment, SegmentList, Vector2D, Point, segment_lists_from_batch

@@ -52,7 +52,7 @@ _EXPORTS = [
     "lsf_set_tie_order", "lsf_capacities", "lsf_cancel_prefetch",
     "lsf_front_end_batch", "lsf_prefetch_batch", "lsf_detect_batch", "lsf_describe_batch", "lsf_project_filter_batch",
     "lsf_knn_hamming", "lsf_pack_kept_records", "lsf_lane_votes", "lsf_map_clear", "lsf_map_add", "lsf_map_size", "lsf_reset_sequence", "lsf_get_tap", "lsf_image_dims",
-    "lsf_last_timings", "lsf_launch_count", "lsf_stream", "lsf_version",
+    "lsf_last_timings", "lsf_launch_count", "lsf_stream", "lsf_version", "lsf_hough_batch",
 ]
 
 _lib = None
@@ -101,6 +101,7 @@ def load():
     lib.lsf_map_append_records.argtypes = [vp, vp, i32, i32, vp, i32, i32]
     lib.lsf_map_read.argtypes = [vp, i32, i32, vp, vp, vp, vp]
     lib.lsf_match_batch.argtypes = [vp, i32, i32, vp, vp]
+    lib.lsf_hough_batch.argtypes = [vp, i32, i32, i32, i32, C.POINTER(LsfSegments)]
     lib.lsf_odometry_init.argtypes = [C.POINTER(LsfOdometry), C.c_double]
     lib.lsf_odometry_step.argtypes = [C.POINTER(LsfOdometry), C.c_double, C.c_double, C.c_double]
     lib.lsf_lane_filter_init.argtypes = [vp, vp]

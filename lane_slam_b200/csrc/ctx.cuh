@@ -36,6 +36,7 @@ struct lsf_ctx {
     int map_n, map_cap;
     void *lane_filter;    // LaneFilterState (lsf_map_exchange.cu), or NULL
     void *jpeg;           // JpegState (k_jpeg.cu), or NULL
+    void *hough;          // HoughState (k_hough.cu), or NULL
     bool events_keep;     // lsf_front_end_batch_jpeg: the batch continues the timing events of the decode stage
     long long jpeg_last_bytes;   // compressed bytes copied to the device by the last lsf_front_end_batch_jpeg
     double *pose_dev; int pose_cap;   // {x, y, cos, sin} per frame, staging of lsf_map_append_records
@@ -110,6 +111,7 @@ int ensure_knn(lsf_ctx *ctx, int nq, int nm, int k);   // ctx->knn_scratch for a
 void mark(lsf_ctx *ctx, const char *name);
 void lane_filter_destroy(lsf_ctx *ctx);                // lsf_map_exchange.cu
 void exchange_destroy(lsf_ctx *ctx);
-void jpeg_destroy(lsf_ctx *ctx);                       // k_jpeg.cu             // timing event on ctx->st
+void jpeg_destroy(lsf_ctx *ctx);
+void hough_destroy(lsf_ctx *ctx);                       // k_jpeg.cu             // timing event on ctx->st
 cudaMemcpyKind out_kind(int mem);
 template <typename T> inline cudaError_t dalloc(T **p, size_t count) { return cudaMalloc((void **)p, (count ? count : 1) * sizeof(T)); }

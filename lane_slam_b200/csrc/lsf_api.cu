@@ -67,6 +67,7 @@ extern "C" int lsf_create(const lsf_config *cfg, lsf_ctx **out)
     memset(&ctx->ex, 0, sizeof(ctx->ex));
     ctx->lane_filter = nullptr;
     ctx->jpeg = nullptr; ctx->jpeg_last_bytes = 0; ctx->events_keep = false;
+    ctx->hough = nullptr;
     ctx->ex.world = 0;
     ctx->knn_scratch = nullptr; ctx->knn_scratch_cap = 0;
     ctx->tap_tmp = nullptr; ctx->tap_cap = 0;
@@ -196,6 +197,7 @@ extern "C" void lsf_destroy(lsf_ctx *ctx)
     exchange_destroy(ctx);
     lane_filter_destroy(ctx);
     jpeg_destroy(ctx);
+    hough_destroy(ctx);
     for (void *p : {(void *)ctx->map_ground, (void *)ctx->map_color, (void *)ctx->map_frame, (void *)ctx->pose_dev}) if (p) cudaFree(p);
     for (int i = 0; i < 2; ++i) if (ctx->staged[i].ev) cudaEventDestroy(ctx->staged[i].ev);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);

@@ -254,6 +254,32 @@ class FrontEnd:
             arrays = a
         return SegmentBatch(n, S, arrays, kk)
 
+    def hough_lines(self, hough_threshold, hough_min_line_length, hough_max_line_gap, ground=True):
+        """LineDetectorHSV.detectLines (line_detector1.py:121-125) for the three colours of every frame of the LAST process() /
+        process_jpeg() call, from that batch's colour masks and edges on the device: cv2.HoughLinesP, normals, endpoint order,
+        wire fields and -- ground=True -- ground projection + line sanity (lsf_hough_batch).  Returns a SegmentBatch of its own
+        arrays (lines_px holds the integer endpoints; no descriptors, no matches)."""
+        n = self._last_n
+        cap = max(1024, 512 * n)
+        while True:
+            a = dict(counts=np.empty((n, 3), np.int32), frame_offset=np.empty((n + 1,), np.int32), color=np.empty((cap,), np.uint8),
+                     lines_px=np.empty((cap, 4), np.float32), normals=np.empty((cap, 2), np.float64), centers=np.empty((cap, 2), np.float32),
+                     pixels_normalized=np.empty((cap, 4), np.float32), normal_f32=np.empty((cap, 2), np.float32),
+                     ground=np.zeros((cap, 4), np.float64), keep=np.zeros((cap,), np.uint8), desc=np.zeros((0, 32), np.uint8))
+            seg = LsfSegments()
+            seg.mem, seg.capacity = MEM_HOST, cap
+            for name in ("counts", "frame_offset", "color", "lines_px", "normals", "centers", "pixels_normalized", "normal_f32", "ground", "keep"):
+                setattr(seg, name, a[name].ctypes.data)
+            rc = self._lib.lsf_hough_batch(self._ctx, int(hough_threshold), int(hough_min_line_length), int(hough_max_line_gap),
+                                           1 if ground else 0, C.byref(seg))
+            if rc == _lib.LSF_E_CAPACITY and seg.n_segments > cap:
+                cap = int(seg.n_segments * 1.25) + 64
+                continue
+            self._check(rc)
+            break
+        a["desc"] = np.zeros((seg.n_segments, 32), np.uint8)
+        return SegmentBatch(n, seg.n_segments, a, 0)
+
     def prefetch(self, frames):
         """Streaming replay: start copying the NEXT batch of host frames (numpy uint8 [n,H,W,3], ideally pinned) to the
         device now; a later process() call with the same array consumes the staged copy (lsf_prefetch_batch)."""

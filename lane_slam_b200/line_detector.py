@@ -83,3 +83,22 @@ class LineDetectorB200(LineDetectorInterface):
 
     def getImage(self):
         return self.bgr
+
+
+class LineDetectorHSVB200(LineDetectorB200):
+    """``line_detector.LineDetectorHSV`` (src/line_detector/include/line_detector/line_detector1.py:11-137), the detector eight of the
+    ten shipped YAML files select: same configuration keys, same setImage / colour filter, lines from cv2.HoughLinesP with the
+    YAML's hough_threshold / hough_min_line_length / hough_max_line_gap.  The Hough transform, the normals and the endpoint
+    ordering run on the GPU (lsf_hough_batch) from the maps setImage left on the device.  lines are int32 like the reference's."""
+
+    def setImage(self, bgr):
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        if bgr.ndim != 3 or bgr.shape[2] != 3:
+            raise ValueError("setImage expects an HxWx3 uint8 BGR image")
+        self.bgr = np.copy(bgr)
+        fe = self._front_end(bgr.shape[:2])
+        fe.process(self.bgr, stages=STAGE_DETECT)          # colour masks + edges (the LSD stage of the batch is not used here)
+        b = fe.hough_lines(self.hough_threshold, self.hough_min_line_length, self.hough_max_line_gap, ground=False)
+        self._batch = dict(counts=b.counts[0].copy(), lines=b.lines_px.astype(np.int32), normals=b.normals.copy(),
+                           centers=b.centers.astype(np.float64))
+        self._area = {}
