@@ -36,17 +36,41 @@ struct Task {
     int max_lines;
 };
 
+// Warp primitives: the device's own; one lane on the host; or -- HP_EMULATE_WARP, test infrastructure (oracle/csrc/hough_check.cpp) --
+// 32 host threads that meet at a barrier for every shuffle, so that the lane protocol below (who computes, who broadcasts, which
+// lane owns which accumulator cell, that every lane reaches every shuffle) runs on a CPU, under a race detector if wanted.
 #if defined(__CUDA_ARCH__)
 #define HP_LANE ((int)(threadIdx.x & 31))
 #define HP_NLANES 32
 #define HP_BCAST(x) __shfl_sync(0xffffffffu, (x), 0)
+#define HP_SHFL_IDX(x, src) __shfl_sync(0xffffffffu, (x), (src))
+#define HP_SHFL_UP(x, o) __shfl_up_sync(0xffffffffu, (x), (o))
+#define HP_SHFL_XOR(x, o) __shfl_xor_sync(0xffffffffu, (x), (o))
 #define HP_SYNC() __syncwarp()
+#define HP_POPC(x) __popc(x)
 HP_FN int cv_round(float v) { return __float2int_rn(v); }
+#elif defined(HP_EMULATE_WARP)
+int hp_emu_lane();                                   // provided by the emulation harness
+int hp_emu_shfl(int value, int src_lane);            // every lane calls it; returns the value lane src_lane passed
+void hp_emu_sync();
+#define HP_LANE hp_emu_lane()
+#define HP_NLANES 32
+#define HP_BCAST(x) hp_emu_shfl((int)(x), 0)
+#define HP_SHFL_IDX(x, src) hp_emu_shfl((int)(x), (src))
+#define HP_SHFL_UP(x, o) hp_emu_shfl((int)(x), hp_emu_lane() >= (o) ? hp_emu_lane() - (o) : hp_emu_lane())
+#define HP_SHFL_XOR(x, o) hp_emu_shfl((int)(x), hp_emu_lane() ^ (o))
+#define HP_SYNC() hp_emu_sync()
+#define HP_POPC(x) __builtin_popcount(x)
+HP_FN int cv_round(float v) { return (int)lrintf(v); }
 #else
 #define HP_LANE 0
 #define HP_NLANES 1
 #define HP_BCAST(x) (x)
+#define HP_SHFL_IDX(x, src) (x)
+#define HP_SHFL_UP(x, o) (x)
+#define HP_SHFL_XOR(x, o) (x)
 #define HP_SYNC() do { } while (0)
+#define HP_POPC(x) __builtin_popcount(x)
 HP_FN int cv_round(float v) { return (int)lrintf(v); }      // cvRound(float) = cvtss2si: to nearest, ties to even
 #endif
 
@@ -80,6 +104,40 @@ HP_FN void vote(const Task &t, int i, int j, int delta, int &best_val, int &best
     }
 }
 
+// Stage 1 of HoughLinesProbabilistic for one task: zero the accumulator, fill the byte mask and list the non-zero points of the
+// bit-plane (bit x & 31 of word [y][x >> 5]) in raster order.  Lane l takes word base + l of every 32-word step; the offsets are a
+// warp prefix sum of the population counts.  Returns the number of points (the same value in every lane).
+HP_FN int collect(const uint32_t *plane, int h, int w, int wp, int32_t *accum, size_t acc_sz, uint8_t *mask, uint32_t *nz)
+{
+    const int lane = HP_LANE;
+    for (size_t k = (size_t)lane; k < acc_sz; k += HP_NLANES) accum[k] = 0;
+    int cnt = 0;
+    const int nwords = h * wp;
+    for (int base = 0; base < nwords; base += HP_NLANES) {
+        const int wi = base + lane;
+        uint32_t bits = 0;
+        int y = 0, x0 = 0, valid = 0;
+        if (wi < nwords) {
+            y = wi / wp; x0 = (wi - y * wp) * 32;
+            valid = w - x0 < 32 ? w - x0 : 32;          // pixels of this word inside the row
+            bits = plane[wi];
+            if (valid < 32) bits &= valid > 0 ? ((1u << valid) - 1u) : 0u;
+        }
+        const int mine = HP_POPC(bits);
+        int incl = mine;
+        for (int o = 1; o < HP_NLANES; o <<= 1) { const int v = HP_SHFL_UP(incl, o); if (lane >= o) incl += v; }
+        int at = cnt + incl - mine;
+        for (int b = 0; b < valid; ++b) {
+            const uint32_t on = (bits >> b) & 1u;
+            mask[(size_t)y * w + x0 + b] = (uint8_t)on;
+            if (on) nz[at++] = ((uint32_t)y << 16) | (uint32_t)(x0 + b);
+        }
+        cnt += HP_SHFL_IDX(incl, HP_NLANES - 1);
+    }
+    HP_SYNC();                                          // accumulator zeroed and lists written by all lanes, read by others next
+    return cnt;
+}
+
 // Returns the number of lines found (all lanes return the same value).  lane 0 owns mask / nzloc / lines.
 HP_FN int hough_lines_p(const Task &t)
 {
@@ -104,12 +162,10 @@ HP_FN int hough_lines_p(const Task &t)
         // update accumulator, find the most probable line
         int max_val = t.threshold - 1, max_n = 0;
         vote(t, i, j, +1, max_val, max_n);
-#if defined(__CUDA_ARCH__)
-        for (int o = 16; o > 0; o >>= 1) {           // largest value, smallest angle among equals = the sequential scan's answer
-            const int v = __shfl_xor_sync(0xffffffffu, max_val, o), n = __shfl_xor_sync(0xffffffffu, max_n, o);
+        for (int o = HP_NLANES / 2; o > 0; o >>= 1) {   // largest value, smallest angle among equals = the sequential scan's answer
+            const int v = HP_SHFL_XOR(max_val, o), n = HP_SHFL_XOR(max_n, o);
             if (v > max_val || (v == max_val && n < max_n)) { max_val = v; max_n = n; }
         }
-#endif
         // if it is too "weak" candidate, continue with another point
         if (max_val < t.threshold) continue;
         // from the current point walk in each direction along the found line and extract the line segment

@@ -57,33 +57,7 @@ __global__ void __launch_bounds__(HOUGH_WARPS_PER_BLOCK * 32) k_hough_p(int h, i
         if (task >= n_tasks) break;
         const int img = task / 3, c = task - img * 3;
         const u32 *plane = planesB + ((size_t)img * PB_COUNT + PB_EC0 + c) * ps;
-        for (size_t k = lane; k < acc_sz; k += 32) accum[k] = 0;
-        // stage 1 of HoughLinesProbabilistic: the non-zero points in raster order, and the mask
-        int cnt = 0;
-        const int nwords = h * wp;
-        for (int base = 0; base < nwords; base += 32) {
-            const int wi = base + lane;
-            u32 bits = 0;
-            int y = 0, x0 = 0, valid = 0;
-            if (wi < nwords) {
-                y = wi / wp; x0 = (wi - y * wp) * 32;
-                valid = min(32, w - x0);                   // pixels of this word inside the row
-                bits = plane[wi];
-                if (valid < 32) bits &= valid > 0 ? ((1u << valid) - 1u) : 0u;
-            }
-            const int mine = __popc(bits);
-            int incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            int at = cnt + incl - mine;
-            for (int b = 0; b < valid; ++b) {
-                const u32 on = (bits >> b) & 1u;
-                mask[(size_t)y * w + x0 + b] = (u8)on;
-                if (on) nz[at++] = ((u32)y << 16) | (u32)(x0 + b);
-            }
-            cnt += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        __syncwarp();                                      // accumulator zeroed and lists written by all lanes, read by others below
+        const int cnt = hp::collect(plane, h, w, wp, accum, acc_sz, mask, nz);
         hp::Task t;
         t.width = w; t.height = h; t.threshold = threshold; t.line_length = line_length; t.line_gap = line_gap;
         t.numrho = numrho; t.trig = trig; t.accum = accum; t.mask = mask; t.nzloc = nz; t.count = cnt;
