@@ -237,7 +237,7 @@ JD_FN void rowmask_flush(uint32_t *rowmask, uint32_t blk, uint32_t rm)
 {
     rm &= 0xfeu;                                         // row 0 holds the DC value: always present
     if (!rm) return;
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) || defined(JD_ATOMIC_ROWMASK)      /* the second: the kernel's source run on host threads (tests) */
     atomicOr(rowmask + (blk >> 2), rm << ((blk & 3) * 8));
 #else
     rowmask[blk >> 2] |= rm << ((blk & 3) * 8);

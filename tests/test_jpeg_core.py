@@ -88,3 +88,57 @@ def test_the_kernels_own_symbol_loop_equals_cv2(sim):
     ref = cv2.imdecode(enc, cv2.IMREAD_COLOR)
     rc, out, _, _ = sim(enc, ref.shape, 0, gpu_loop=True)
     assert rc == 0 and np.array_equal(out, ref)
+
+
+def _tsan_runtime():
+    p = subprocess.run(["g++", "-print-file-name=libtsan.so"], capture_output=True, text=True).stdout.strip()
+    return p if os.path.isabs(p) and os.path.exists(p) else None
+
+
+def test_huffman_kernel_source_runs_on_host_threads(tmp_path):
+    """The REAL source text of k_jpeg_huff, cut out of k_jpeg.cu and run as a block of host threads (oracle/jpeg_huff_emu.py,
+    oracle/csrc/cuda_threads_emu.h): un-stuffing, Huffman rounds with compaction, scans, coefficient writes and DC prediction
+    reproduce cv2.imdecode -- with 64 and with 512 threads per image."""
+    import sys
+    from oracle import jpeg_huff_emu as J
+    for jt, big in ((64, True), (512, False)):
+        d = tmp_path / ("jt%d" % jt)
+        d.mkdir()
+        so = J.build(str(d), jt=jt)
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "jpeg_huff_emu_run.py"), so] + (["big"] if big else []),
+                             capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0 and "emulated k_jpeg_huff ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_huffman_kernel_has_no_shared_memory_race(tmp_path):
+    """The same build under ThreadSanitizer: the barriers are the only synchronisation between the host threads, so every
+    shared-memory access pair a missing __syncthreads leaves unordered is reported (the CPU stand-in for compute-sanitizer
+    racecheck).  Control: with the ordering this kernel shipped with for one day -- the 'changed' flag cleared BEFORE the barrier at
+    the top of a re-decode round, while the next warp may still be reading it -- the detector must fire."""
+    import sys
+    from oracle import jpeg_huff_emu as J
+    rt = _tsan_runtime()
+    if rt is None:
+        pytest.skip("no ThreadSanitizer runtime")
+    env = dict(os.environ, LD_PRELOAD=rt, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0")
+
+    def run(so, *more):
+        return subprocess.run([sys.executable, os.path.join(ROOT, "tests", "jpeg_huff_emu_run.py"), so] + list(more), capture_output=True, text=True,
+                              timeout=1200, env=env)
+    good = tmp_path / "good"; good.mkdir()
+    out = run(J.build(str(good), jt=512, sanitize=True), "big")          # the shipped block size, real 640x480 camera frames included
+    assert out.returncode == 0 and "emulated k_jpeg_huff ok" in out.stdout, out.stderr[-3000:]
+    assert "ThreadSanitizer" not in out.stderr, out.stderr[-3000:]
+    # control
+    fixed = "        __syncthreads();\n        s_chg[t] = 0;"
+    text = J.kernel_text()
+    assert fixed in text
+    orig = J.kernel_text
+    J.kernel_text = lambda: text.replace(fixed, "        s_chg[t] = 0;\n        __syncthreads();", 1)
+    try:
+        bad = tmp_path / "bad"; bad.mkdir()
+        so = J.build(str(bad), jt=64, sanitize=True)
+    finally:
+        J.kernel_text = orig
+    out = run(so)
+    assert "WARNING: ThreadSanitizer: data race" in out.stderr and "k_jpeg_huff" in out.stderr
