@@ -10,18 +10,18 @@ thread_local cuemu::Idx threadIdx, blockIdx;
 cuemu::Idx blockDim, gridDim;
 
 namespace {
-struct Start { int tid, block; void (*body)(void *); void *arg; };
+struct Start { int tid, block, block_y; void (*body)(void *); void *arg; };
 void *thread_main(void *p)
 {
     Start *s = (Start *)p;
     threadIdx = cuemu::Idx{(unsigned)s->tid, 0, 0};
-    blockIdx = cuemu::Idx{(unsigned)s->block, 0, 0};
+    blockIdx = cuemu::Idx{(unsigned)s->block, (unsigned)s->block_y, 0};
     s->body(s->arg);
     return nullptr;
 }
 }  // namespace
 
-void cuemu_run_block(int nthreads, int block, void (*body)(void *), void *arg)
+void cuemu_run_block(int nthreads, int block, void (*body)(void *), void *arg, int block_y)
 {
     cuemu::n_threads = nthreads;
     blockDim = cuemu::Idx{(unsigned)nthreads, 1, 1};
@@ -33,7 +33,7 @@ void cuemu_run_block(int nthreads, int block, void (*body)(void *), void *arg)
     pthread_attr_init(&at);
     pthread_attr_setstacksize(&at, 1 << 20);
     for (int t = 0; t < nthreads; ++t) {
-        st[t] = Start{t, block, body, arg};
+        st[t] = Start{t, block, block_y, body, arg};
         if (pthread_create(&th[t], &at, thread_main, &st[t])) { fprintf(stderr, "cuemu: pthread_create failed\n"); abort(); }
     }
     for (int t = 0; t < nthreads; ++t) pthread_join(th[t], nullptr);

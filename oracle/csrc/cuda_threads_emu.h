@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 
 #define __global__
 #define __device__
@@ -84,5 +85,7 @@ static inline int max(int a, int b) { return a > b ? a : b; }
 // shared-memory "addresses" of the kernels' inline-PTX loads: the low 32 bits of the host address of a static object
 static inline uint32_t __cvta_generic_to_shared(const void *p) { return (uint32_t)(uintptr_t)p; }
 
-// run `body(arg)` as one block of nthreads threads (a multiple of 32) with blockIdx.x = block
-void cuemu_run_block(int nthreads, int block, void (*body)(void *), void *arg);
+static inline int __float2int_rn(float v) { return (int)lrintf(v); }
+
+// run `body(arg)` as one block of nthreads threads (a multiple of 32) with blockIdx = (block, block_y); gridDim is the caller's to set
+void cuemu_run_block(int nthreads, int block, void (*body)(void *), void *arg, int block_y = 0);

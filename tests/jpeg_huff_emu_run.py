@@ -11,6 +11,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import cv2
 import numpy as np
 
+cv2.setNumThreads(1)          # OpenCV's own worker threads are not instrumented: under ThreadSanitizer they only add noise
+
 import realset
 from oracle import synth
 

@@ -120,7 +120,7 @@ def test_huffman_kernel_has_no_shared_memory_race(tmp_path):
     rt = _tsan_runtime()
     if rt is None:
         pytest.skip("no ThreadSanitizer runtime")
-    env = dict(os.environ, LD_PRELOAD=rt, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0")
+    env = dict(os.environ, LD_PRELOAD=rt, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0 history_size=7")
 
     def run(so, *more):
         return subprocess.run([sys.executable, os.path.join(ROOT, "tests", "jpeg_huff_emu_run.py"), so] + list(more), capture_output=True, text=True,
@@ -140,5 +140,10 @@ def test_huffman_kernel_has_no_shared_memory_race(tmp_path):
         so = J.build(str(bad), jt=64, sanitize=True)
     finally:
         J.kernel_text = orig
-    out = run(so)
-    assert "WARNING: ThreadSanitizer: data race" in out.stderr and "k_jpeg_huff" in out.stderr
+    seen = False
+    for _ in range(3):          # the detector keeps a bounded history per memory cell: give it three runs to catch the pair
+        out = run(so)
+        if "WARNING: ThreadSanitizer: data race" in out.stderr and "k_jpeg_huff" in out.stderr:
+            seen = True
+            break
+    assert seen, out.stderr[-2000:]
