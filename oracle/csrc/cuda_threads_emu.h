@@ -86,6 +86,11 @@ static inline int max(int a, int b) { return a > b ? a : b; }
 static inline uint32_t __cvta_generic_to_shared(const void *p) { return (uint32_t)(uintptr_t)p; }
 
 static inline int __float2int_rn(float v) { return (int)lrintf(v); }
+struct alignas(8) uint2 { unsigned x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+template <typename T> static inline T __ldg(const T *p) { return *p; }
 
 // run `body(arg)` as one block of nthreads threads (a multiple of 32) with blockIdx = (block, block_y); gridDim is the caller's to set
 void cuemu_run_block(int nthreads, int block, void (*body)(void *), void *arg, int block_y = 0);

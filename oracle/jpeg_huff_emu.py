@@ -1,6 +1,7 @@
-"""TEST INFRASTRUCTURE: builds a host library that runs the REAL source text of k_jpeg_huff (lane_slam_b200/csrc/k_jpeg.cu: byte
-un-stuffing, the self-synchronising Huffman rounds with their compaction, prefix sums, coefficient writes, DC prediction) as one
-thread block made of host threads (oracle/csrc/cuda_threads_emu.h), followed by the host IDCT / colour code of the shared header.
+"""TEST INFRASTRUCTURE: builds a host library that runs the REAL source text of the kernels of lane_slam_b200/csrc/k_jpeg.cu --
+k_jpeg_huff (byte un-stuffing, the self-synchronising Huffman rounds with their compaction, prefix sums, coefficient writes, DC
+prediction), k_jpeg_idct (flagged rows only, zeroed behind the read) and k_jpeg_color_420 / k_jpeg_color -- as thread blocks made of
+host threads (oracle/csrc/cuda_threads_emu.h), with the grids lsf_front_end_batch_jpeg launches.
 The kernel text is cut out of the .cu file at build time, so the test always runs what ships; only the two inline-PTX shared-memory
 loads are replaced by plain loads.  With sanitize=True the library is built with ThreadSanitizer: the barriers are the only
 synchronisation between the threads, so it reports the races a missing __syncthreads leaves."""
@@ -32,6 +33,24 @@ static void body(void *p)
     lsf::k_jpeg_huff(l->g, l->blob, l->items, l->tabs, l->clean, l->clean_words, l->coef, l->coef_per_img, l->dcdiff, l->rowmask, l->status);
 }
 
+struct IdctArgs { jd::Image g; int n; int16_t *coef; size_t coef_per_img; const u32 *rowmask; const u16 *qtabs; u8 *plane; size_t plane_per_img; };
+static void body_idct(void *p)
+{
+    IdctArgs *a = (IdctArgs *)p;
+    lsf::k_jpeg_idct(a->g, a->n, a->coef, a->coef_per_img, a->rowmask, a->qtabs, a->plane, a->plane_per_img);
+}
+struct ColorArgs { jd::Image g; int n; const u8 *plane; size_t plane_per_img; u8 *bgr; size_t frame_bytes; };
+static void body_color420(void *p)
+{
+    ColorArgs *a = (ColorArgs *)p;
+    lsf::k_jpeg_color_420(a->g, a->n, a->plane, a->plane_per_img, a->bgr, a->frame_bytes);
+}
+static void body_color(void *p)
+{
+    ColorArgs *a = (ColorArgs *)p;
+    lsf::k_jpeg_color(a->g, a->n, a->plane, a->plane_per_img, a->bgr, a->frame_bytes);
+}
+
 // data: one JPEG file.  bgr: [H][W][3] out.  Returns 0, < 0 for a file outside the decoder's scope, 100 + status if the kernel
 // flagged the image.  prefill: the byte the stream buffer is filled with first (the kernel's buffer holds an older image).
 extern "C" __attribute__((visibility("default")))
@@ -52,31 +71,31 @@ int jhe_decode(const uint8_t *data, size_t len, uint8_t *bgr, int prefill)
     Launch l = {im, data, &item, &tabs, clean.data(), clean_words, coef.data(), coef_per_img, dcdiff.data(), rowmask.data(), &status};
     cuemu_run_block(lsf::JT, 0, body, &l);
     if (status) return 100 + status;
-    // k_jpeg_idct / k_jpeg_color on the host (the shared header's functions; rows the Huffman pass did not flag are not read)
-    std::vector<std::vector<uint8_t>> plane(3);
-    for (int c = 0; c < im.ncomp; ++c) plane[c].assign((size_t)im.bw[c] * im.bh[c] * 64, 0);
-    for (size_t b = 0; b < nblocks; ++b) {
-        const int slot = (int)(b % im.bpm), mcu = (int)(b / im.bpm), c = im.slot_comp[slot];
-        const int bx = (mcu % im.mcux) * im.hs[c] + im.slot_bx[slot], by = (mcu / im.mcux) * im.vs[c] + im.slot_by[slot];
-        const u32 rows = ((rowmask[b >> 2] >> ((b & 3) * 8)) & 0xfeu) | 1u;
-        int16_t blk[64];
-        for (int k = 0; k < 64; ++k) blk[k] = ((rows >> (k >> 3)) & 1) ? coef[b * 64 + k] : (int16_t)0x5a5a;
-        for (int k = 8; k < 64; ++k) if (!((rows >> (k >> 3)) & 1) && coef[b * 64 + k] != 0) return -6;
-        jd::idct_block_rows(blk, im.q[c], rows, &plane[c][((size_t)by * 8) * (im.bw[c] * 8) + bx * 8], im.bw[c] * 8);
+    // k_jpeg_idct: grid (ceil(blocks / 32), n) x 256 threads
+    size_t plane_bytes = 0;
+    for (int c = 0; c < im.ncomp; ++c) plane_bytes += (size_t)im.bw[c] * im.bh[c] * 64;
+    const size_t plane_per_img = (plane_bytes + 15) & ~(size_t)15;
+    std::vector<u8> plane(plane_per_img, 0x99);
+    std::vector<u16> qtabs(192);
+    memcpy(qtabs.data(), im.q, 192 * sizeof(u16));
+    IdctArgs ia = {im, 1, coef.data(), coef_per_img, rowmask.data(), qtabs.data(), plane.data(), plane_per_img};
+    const int gx = (int)((nblocks + 31) / 32);
+    gridDim = cuemu::Idx{(unsigned)gx, 1, 1};
+    for (int b = 0; b < gx; ++b) cuemu_run_block(256, b, body_idct, &ia, 0);
+    for (size_t k = 0; k < coef_per_img; ++k) if (coef[k] != 0) return -7;       // the kernel leaves the coefficient buffer zero
+    // colour: the 4:2:0 kernel where lsf_front_end_batch_jpeg uses it, else the generic one
+    const size_t frame_bytes = (size_t)im.W * im.H * 3;
+    ColorArgs ca = {im, 1, plane.data(), plane_per_img, bgr, frame_bytes};
+    if (im.ncomp == 3 && im.hs[0] == 2 && im.vs[0] == 2 && (im.W & 7) == 0 && (frame_bytes & 7) == 0) {
+        const int npx8 = im.H * (im.W / 8), cx = (npx8 + 255) / 256;
+        gridDim = cuemu::Idx{(unsigned)cx, 1, 1};
+        for (int b = 0; b < cx; ++b) cuemu_run_block(256, b, body_color420, &ca, 0);
+    } else {
+        const long long npx4 = (long long)im.H * ((im.W + 3) / 4);
+        const int cx = (int)((npx4 + 255) / 256);
+        gridDim = cuemu::Idx{(unsigned)cx, 1, 1};
+        for (int b = 0; b < cx; ++b) cuemu_run_block(256, b, body_color, &ca, 0);
     }
-    for (int y = 0; y < im.H; ++y)
-        for (int x = 0; x < im.W; ++x) {
-            uint8_t *o = bgr + ((size_t)y * im.W + x) * 3;
-            const int yy = plane[0][(size_t)y * im.bw[0] * 8 + x];
-            if (im.ncomp == 1) { o[0] = o[1] = o[2] = (uint8_t)yy; continue; }
-            int cc[3] = {yy, 0, 0};
-            for (int c = 1; c < 3; ++c) {
-                const int hs = im.hmax / im.hs[c], vs = im.vmax / im.vs[c];
-                const int dw = (im.W * im.hs[c] + im.hmax - 1) / im.hmax, dh = (im.H * im.vs[c] + im.vmax - 1) / im.vmax;
-                cc[c] = jd::chroma_at(plane[c].data(), im.bw[c] * 8, dw, dh, hs, vs, x, y);
-            }
-            jd::ycc_to_bgr(cc[0], cc[1], cc[2], o);
-        }
     return 0;
 }
 '''
@@ -84,7 +103,7 @@ int jhe_decode(const uint8_t *data, size_t len, uint8_t *bgr, int prefill)
 
 def kernel_text():
     text = open(os.path.join(CSRC, "k_jpeg.cu")).read()
-    body = text[text.index("namespace lsf {"):text.index("// plane layout of one image")]
+    body = text[text.index("namespace lsf {"):text.index("}  // namespace lsf")]
     body, n = re.subn(r"__device__ __forceinline__ u32 lds32\(u32 a\) \{[^\n]*\}\n", "", body)
     assert n == 1, "the inline-PTX shared-memory load of k_jpeg.cu was not found"
     assert "asm volatile" not in body
