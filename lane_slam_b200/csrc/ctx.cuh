@@ -108,10 +108,10 @@ inline int fail(lsf_ctx *ctx, int code, const std::string &msg)
 // helpers defined in lsf_api.cu
 int stage_in(lsf_ctx *ctx, size_t bytes);              // ctx->seg_in scratch of at least `bytes`
 int ensure_knn(lsf_ctx *ctx, int nq, int nm, int k);   // ctx->knn_scratch for a (nq x nm, k) search
-void mark(lsf_ctx *ctx, const char *name);
+void mark(lsf_ctx *ctx, const char *name);              // timing event on ctx->st
 void lane_filter_destroy(lsf_ctx *ctx);                // lsf_map_exchange.cu
 void exchange_destroy(lsf_ctx *ctx);
-void jpeg_destroy(lsf_ctx *ctx);
-void hough_destroy(lsf_ctx *ctx);                       // k_jpeg.cu             // timing event on ctx->st
+void jpeg_destroy(lsf_ctx *ctx);                       // k_jpeg.cu
+void hough_destroy(lsf_ctx *ctx);                      // k_hough.cu
 cudaMemcpyKind out_kind(int mem);
 template <typename T> inline cudaError_t dalloc(T **p, size_t count) { return cudaMalloc((void **)p, (count ? count : 1) * sizeof(T)); }
