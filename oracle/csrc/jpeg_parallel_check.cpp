@@ -192,3 +192,13 @@ static int jpc_decode_mode(const uint8_t *data, size_t len, uint8_t *bgr, int su
     if (nsub_out) *nsub_out = nsub;
     return 0;
 }
+
+// geometry of a file as jd::parse sees it (callers size the output of jpc_decode* from it); returns parse()'s code
+extern "C" __attribute__((visibility("default")))
+int jpc_info(const uint8_t *data, size_t len, int *W, int *H)
+{
+    jd::Image im;
+    const int rc = jd::parse(data, len, im, nullptr);
+    if (rc == 0) { *W = im.W; *H = im.H; }
+    return rc;
+}

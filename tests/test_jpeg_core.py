@@ -148,3 +148,20 @@ def test_huffman_kernel_has_no_shared_memory_race(tmp_path):
             seen = True
             break
     assert seen, out.stderr[-2000:]
+
+
+def test_malformed_files_never_reach_out_of_bounds(tmp_path):
+    """600 mutated files (flipped header bytes, truncations, flipped entropy bytes, garbage) through jd::parse -- the host-side step
+    of lsf_front_end_batch_jpeg -- and the decoder's logic under AddressSanitizer: an error code or some image, no stray access."""
+    import sys
+    rt = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not (os.path.isabs(rt) and os.path.exists(rt)):
+        pytest.skip("no AddressSanitizer runtime")
+    so = str(tmp_path / "libjpc_asan.so")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-g", "-fsanitize=address,bounds,null,alignment", "-shared", "-fPIC", "-o", so,
+                           os.path.join(ROOT, "oracle", "csrc", "jpeg_parallel_check.cpp")])
+    env = dict(os.environ, LD_PRELOAD=rt, ASAN_OPTIONS="detect_leaks=0")
+    for seed in (11, 12):
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "jpeg_fuzz_run.py"), so, str(seed), "300"], capture_output=True, text=True,
+                             timeout=1200, env=env)
+        assert out.returncode == 0 and "fuzz ok" in out.stdout and "ERROR: AddressSanitizer" not in out.stderr, out.stderr[-3000:]
