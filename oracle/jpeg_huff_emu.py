@@ -111,13 +111,15 @@ def kernel_text():
 
 
 def build(out_dir, jt=64, sanitize=False):
+    """sanitize: False, True / "thread" (ThreadSanitizer) or "address" (AddressSanitizer + bounds)."""
     src = os.path.join(out_dir, "jpeg_huff_emu.cpp")
     with open(src, "w") as f:
         f.write(HARNESS.replace("@@KERNEL@@", kernel_text()))
-    so = os.path.join(out_dir, "libjhe%s.so" % ("_tsan" if sanitize else ""))
+    kind = "thread" if sanitize is True else sanitize
+    so = os.path.join(out_dir, "libjhe%s.so" % ("_%s" % kind if kind else ""))
     cmd = ["g++", "-std=c++14", "-O1" if sanitize else "-O2", "-g", "-shared", "-fPIC", "-pthread", "-DLSF_JT=%d" % jt,
            "-I", os.path.join(ROOT, "oracle", "csrc"), "-I", CSRC, src, os.path.join(ROOT, "oracle", "csrc", "cuda_threads_emu.cpp"), "-o", so]
-    if sanitize:
-        cmd.insert(1, "-fsanitize=thread")
+    if kind:
+        cmd.insert(1, "-fsanitize=thread" if kind == "thread" else "-fsanitize=address,bounds")
     subprocess.check_call(cmd)
     return so

@@ -165,3 +165,10 @@ def test_malformed_files_never_reach_out_of_bounds(tmp_path):
         out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "jpeg_fuzz_run.py"), so, str(seed), "300"], capture_output=True, text=True,
                              timeout=1200, env=env)
         assert out.returncode == 0 and "fuzz ok" in out.stdout and "ERROR: AddressSanitizer" not in out.stderr, out.stderr[-3000:]
+    # the kernels themselves (their real source on host threads) on corrupted entropy data
+    from oracle import jpeg_huff_emu as J
+    d = tmp_path / "emu"; d.mkdir()
+    so = J.build(str(d), jt=64, sanitize="address")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "jpeg_kernel_fuzz_run.py"), so, "5", "80"], capture_output=True, text=True,
+                         timeout=1200, env=env)
+    assert out.returncode == 0 and "kernel fuzz ok" in out.stdout and "ERROR: AddressSanitizer" not in out.stderr, out.stderr[-3000:]
