@@ -52,7 +52,8 @@ static void body_color(void *p)
 }
 
 // data: one JPEG file.  bgr: [H][W][3] out.  Returns 0, < 0 for a file outside the decoder's scope, 100 + status if the kernel
-// flagged the image.  prefill: the byte the stream buffer is filled with first (the kernel's buffer holds an older image).
+// flagged the image.  prefill: low byte = what the stream buffer is filled with first (the kernel's buffer holds an older image);
+// bit 8: stop after the Huffman pass (bgr is not written).
 extern "C" __attribute__((visibility("default")))
 int jhe_decode(const uint8_t *data, size_t len, uint8_t *bgr, int prefill)
 {
@@ -71,6 +72,7 @@ int jhe_decode(const uint8_t *data, size_t len, uint8_t *bgr, int prefill)
     Launch l = {im, data, &item, &tabs, clean.data(), clean_words, coef.data(), coef_per_img, dcdiff.data(), rowmask.data(), &status};
     cuemu_run_block(lsf::JT, 0, body, &l);
     if (status) return 100 + status;
+    if (prefill & 0x100) return 0;       // Huffman pass only (race detection on a large frame without the other kernels' thread spawning)
     // k_jpeg_idct: grid (ceil(blocks / 32), n) x 256 threads
     size_t plane_bytes = 0;
     for (int c = 0; c < im.ncomp; ++c) plane_bytes += (size_t)im.bw[c] * im.bh[c] * 64;

@@ -29,6 +29,8 @@ for it in range(int(sys.argv[3])):
     for _ in range(rng.integers(1, 30)):
         b[rng.integers(650, len(b) - 2)] = rng.integers(0, 256)          # entropy-coded bytes only
     out = np.zeros(shapes[k], np.uint8)
-    rc = lib.jhe_decode(b.ctypes.data_as(C.c_void_p), C.c_size_t(len(b)), out.ctypes.data_as(C.c_void_p), 0xFF)
+    # the first two files go through all kernels, the rest through the Huffman pass only (the other kernels' accesses do not
+    # depend on the data; spawning their thousands of threads under the sanitizer is what takes the time)
+    rc = lib.jhe_decode(b.ctypes.data_as(C.c_void_p), C.c_size_t(len(b)), out.ctypes.data_as(C.c_void_p), 0xFF | (0 if it < 2 else 0x100))
     codes[rc] = codes.get(rc, 0) + 1
 print("kernel fuzz ok", codes)
