@@ -796,9 +796,9 @@ def test_hough_detector_isolated():
     import sys
     script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gpu_hough_check.py")
     try:
-        out = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=900)
+        out = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=300)
     except subprocess.TimeoutExpired:
-        pytest.xfail("gpu_hough_check.py did not finish in 900 s (first GPU run of k_hough.cu)")
+        pytest.xfail("gpu_hough_check.py did not finish in 300 s (first GPU run of k_hough.cu)")
     if out.returncode != 0:
         pytest.xfail("first GPU run of k_hough.cu failed:\n" + (out.stdout + out.stderr)[-3000:])
     assert "hough check ok" in out.stdout
